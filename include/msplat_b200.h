@@ -1,0 +1,122 @@
+/*
+ * msplat_b200.h -- C ABI of libmsplat_b200.so: the B200-native (sm_100a) replacement for the
+ * 12-function pybind11 module `msplat._C` of pointrix-project/msplat
+ * (/root/reference/msplat/src/ext.cpp:13-26; prototypes /root/reference/msplat/include/*.h).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named *_host;
+ *  - the caller owns all memory: outputs and workspaces are allocated by the caller (the Python
+ *    side uses torch's stream-ordered caching allocator); the library never allocates, frees or
+ *    synchronises, keeps no mutable global state and is re-entrant;
+ *  - `stream` is a cudaStream_t; kernels run on the caller's current device;
+ *  - return value: 0 = success, > 0 = cudaError_t of a failed launch, < 0 = argument error
+ *    (-1 bad argument / misalignment, -2 workspace too small, -3 size out of range);
+ *    msb_last_error() returns a thread-local description;
+ *  - float tensors are float32, row-major contiguous and 16-byte aligned at their base;
+ *    `visible` is one byte per Gaussian (torch.bool), NULL = all visible;
+ *  - outputs for culled / invisible / degenerate Gaussians are written as zeros (the reference
+ *    relies on torch::zeros pre-initialisation), so the caller may pass uninitialised buffers.
+ */
+#ifndef MSPLAT_B200_H
+#define MSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int msb_version(void);
+int msb_sm_count(void);
+const char* msb_last_error(void);
+
+/* ---- project_point ------------------------------------------------------------------------
+ * replaces projectPointsForward  (include/project_point.h, src/project_point.cu:147-179)
+ *          projectPointsBackward (src/project_point.cu:181-228)
+ * xyz [P,3], intr [4] = fx fy cx cy, extr first 12 floats of [3,4]/[4,4]; uv [P,2], depth [P].
+ * dL_dintr [4] / dL_dextr [12] may be NULL (gradient not wanted); otherwise they must be
+ * zero-initialised by the caller and are accumulated into. */
+int msb_project_point_fwd(const float* xyz, const float* intr, const float* extr, int P, int W, int H,
+                          float nearest, float extent, float* uv, float* depth, void* stream);
+int msb_project_point_bwd(const float* xyz, const float* intr, const float* extr, const float* depth,
+                          const float* dL_duv, const float* dL_ddepth, int P, float* dL_dxyz, float* dL_dintr,
+                          float* dL_dextr, void* stream);
+
+/* ---- compute_cov3d ------------------------------------------------------------------------
+ * replaces computeCov3DForward / computeCov3DBackward (src/compute_cov3d.cu:149-200)
+ * scale [P,3], quat [P,4] (r,x,y,z, not normalised), cov3d [P,6] upper triangle. */
+int msb_compute_cov3d_fwd(const float* scale, const float* quat, const uint8_t* visible, int P, float* cov3d,
+                          void* stream);
+int msb_compute_cov3d_bwd(const float* scale, const float* quat, const uint8_t* visible, const float* dL_dcov3d,
+                          int P, float* dL_dscale, float* dL_dquat, void* stream);
+
+/* ---- ewa_project --------------------------------------------------------------------------
+ * replaces EWAProjectForward / EWAProjectBackward (src/ewa_project.cu:254-345)
+ * conic [P,3], radius [P] int32, tiles [P] int32 -- radius and tiles are bit-exact with the
+ * reference's sm_100 build. */
+int msb_ewa_project_fwd(const float* xyz, const float* cov3d, const float* intr, const float* extr,
+                        const float* uv, const uint8_t* visible, int P, int W, int H, float* conic,
+                        int32_t* radius, int32_t* tiles, void* stream);
+int msb_ewa_project_bwd(const float* xyz, const float* cov3d, const float* intr, const float* extr,
+                        const int32_t* radius, const float* dL_dconic, int P, float* dL_dxyz, float* dL_dcov3d,
+                        float* dL_dintr, float* dL_dextr, void* stream);
+
+/* ---- fused per-Gaussian stage of rasterization() (msplat/__init__.py:70-81) ------------------
+ * project + (visible = depth != 0) + cov3d + ewa in one pass; backward = ewa^T, cov3d^T, project^T.
+ * dL_ddepth may be NULL. */
+int msb_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* intr,
+                       const float* extr, int P, int W, int H, float nearest, float extent, float* uv,
+                       float* depth, float* conic, int32_t* radius, int32_t* tiles, void* stream);
+int msb_preprocess_bwd(const float* xyz, const float* scale, const float* quat, const float* intr,
+                       const float* extr, const float* depth, const int32_t* radius, const float* dL_duv,
+                       const float* dL_ddepth, const float* dL_dconic, int P, float* dL_dxyz, float* dL_dscale,
+                       float* dL_dquat, float* dL_dintr, float* dL_dextr, void* stream);
+
+/* ---- compute_sh ---------------------------------------------------------------------------
+ * replaces computeSHForward / computeSHBackward (src/compute_sh.cu:1696-1754)
+ * shs [P,Cs,D] (D = (deg+1)^2, deg 0..10, D innermost), dirs [P,3], value [P,Cs]. */
+int msb_compute_sh_fwd(const float* shs, const float* dirs, const uint8_t* visible, int P, int Cs, int D,
+                       float* value, void* stream);
+int msb_compute_sh_bwd(const float* shs, const float* dirs, const uint8_t* visible, const float* dL_dvalue,
+                       int P, int Cs, int D, float* dL_dshs, float* dL_ddirs, void* stream);
+
+/* ---- sort_gaussian ------------------------------------------------------------------------
+ * replaces torch.cumsum + computeGaussianKey + torch.sort + torch.gather +
+ * computeTileGaussianRange (msplat/sort_gaussian.py:42-52, src/sort_gaussian.cu:74-142).
+ * Two phases because M = sum(tiles) sizes the output:
+ *   1. msb_sort_scan: offsets[P] = inclusive int32 cumsum of tiles; the int64 total is copied
+ *      asynchronously to *total_host (PINNED host memory) -- synchronise `stream` before reading;
+ *   2. msb_sort_gaussian: key duplication, onesweep radix sort over 32 + ceil(log2 T) bits,
+ *      tile ranges.  idx_sorted [M] int32, tile_range [T,2] int32 (empty tiles (0,0)). */
+size_t msb_sort_scan_workspace_bytes(int P);
+int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* total_host, void* ws,
+                  size_t ws_bytes, void* stream);
+int msb_sort_num_passes(int W, int H);
+size_t msb_sort_workspace_bytes(long long M, int W, int H);
+int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles,
+                      const int32_t* offsets, int P, long long M, int W, int H, int32_t* idx_sorted,
+                      int32_t* tile_range, void* ws, size_t ws_bytes, int sm_count, void* stream);
+
+/* ---- alpha_blending -----------------------------------------------------------------------
+ * replaces alphaBlendingForward / alphaBlendingBackward (src/alpha_blending.cu:248-573)
+ * feature [P,C] row-major (the Python-level layout); image [C,H,W]; final_T [H,W];
+ * ncontrib [H,W] int32.  `packed` (msb_blend_fwd_workspace_bytes) is written by the forward
+ * call and must be handed unchanged to the backward call; `ws` (msb_blend_bwd_workspace_bytes)
+ * is scratch.  dL_dfeature is contiguous [P,C]. */
+int msb_blend_cpad(int C);
+size_t msb_blend_fwd_workspace_bytes(int P, int C);
+size_t msb_blend_bwd_workspace_bytes(int P, int C);
+int msb_alpha_blending_fwd(const float* uv, const float* conic, const float* opacity, const float* feature,
+                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int P, int C, int W,
+                           int H, float* image, float* final_T, int32_t* ncontrib, void* packed,
+                           size_t packed_bytes, void* stream);
+int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, const int32_t* tile_range, float bg,
+                           int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
+                           const float* dL_dimage, const void* packed, float* dL_duv, float* dL_dconic,
+                           float* dL_dopacity, float* dL_dfeature, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSPLAT_B200_H */

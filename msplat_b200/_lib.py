@@ -1,0 +1,173 @@
+"""ctypes binding of libmsplat_b200.so (the C ABI declared in include/msplat_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a
+tensor is not on a CUDA device the call raises.  PyTorch is used for device memory, streams
+and autograd plumbing only; every kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmsplat_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+# Per-process launch counter: bench.py reports it as "gpu_launches".
+_launches = 0
+
+# kernels launched by each C-ABI entry point (see csrc/*.cu); a tuple means (fixed, per-pass)
+_KERNELS_PER_CALL = {}
+
+
+def _declare(lib):
+    P, F, I, V, SZ, LL = c_void_p, c_float, c_int, c_void_p, c_size_t, c_longlong
+    sig = {
+        "msb_version": (c_int, []),
+        "msb_sm_count": (c_int, []),
+        "msb_last_error": (ctypes.c_char_p, []),
+        "msb_project_point_fwd": (I, [P, P, P, I, I, I, F, F, P, P, V]),
+        "msb_project_point_bwd": (I, [P, P, P, P, P, P, I, P, P, P, V]),
+        "msb_compute_cov3d_fwd": (I, [P, P, P, I, P, V]),
+        "msb_compute_cov3d_bwd": (I, [P, P, P, P, I, P, P, V]),
+        "msb_ewa_project_fwd": (I, [P, P, P, P, P, P, I, I, I, P, P, P, V]),
+        "msb_ewa_project_bwd": (I, [P, P, P, P, P, P, I, P, P, P, P, V]),
+        "msb_preprocess_fwd": (I, [P, P, P, P, P, I, I, I, F, F, P, P, P, P, P, V]),
+        "msb_preprocess_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, V]),
+        "msb_compute_sh_fwd": (I, [P, P, P, I, I, I, P, V]),
+        "msb_compute_sh_bwd": (I, [P, P, P, P, I, I, I, P, P, V]),
+        "msb_sort_scan_workspace_bytes": (SZ, [I]),
+        "msb_sort_scan": (I, [P, I, P, P, P, SZ, V]),
+        "msb_sort_num_passes": (I, [I, I]),
+        "msb_sort_workspace_bytes": (SZ, [LL, I, I]),
+        "msb_sort_gaussian": (I, [P, P, P, P, P, I, LL, I, I, P, P, P, SZ, I, V]),
+        "msb_blend_cpad": (I, [I]),
+        "msb_blend_fwd_workspace_bytes": (SZ, [I, I]),
+        "msb_blend_bwd_workspace_bytes": (SZ, [I, I]),
+        "msb_alpha_blending_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P, P, P, P, SZ, V]),
+        "msb_alpha_blending_bwd": (I, [P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, SZ, V]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"msplat_b200: {LIB_PATH} is missing. Build the CUDA library first "
+                        "(python -m msplat_b200.build); there is no CPU or PyTorch fallback."
+                    )
+                L = ctypes.CDLL(LIB_PATH)
+                _declare(L)
+                _lib = L
+    return _lib
+
+
+def exported_symbols():
+    """Names declared in include/msplat_b200.h that the library must export."""
+    return sorted(_declare(lib()).keys())
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().msb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"msplat_b200.{what} failed (code {rc}): {msg}")
+
+
+def count_launches(n: int):
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor plumbing
+# ------------------------------------------------------------------------------------------------
+
+def stream_ptr(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def as_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    """contiguous float32 CUDA tensor, 16-byte aligned (the reference calls .contiguous() too)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")  # reference: CHECK_CUDA, include/utils.h:9-10
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def as_i32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.int32:
+        raise RuntimeError(f"{name} must be int32, got {t.dtype}")
+    return t.contiguous()
+
+
+def as_mask(t: torch.Tensor, name: str, n: int) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.bool:
+        raise RuntimeError(f"{name} must be bool, got {t.dtype}")
+    t = t.contiguous()
+    if t.numel() != n:
+        raise RuntimeError(f"{name} must have {n} elements, got {t.numel()}")
+    return t
+
+
+_pinned = threading.local()
+
+
+def pinned_i64(device) -> torch.Tensor:
+    """A per-thread, per-device pinned int64[1] used for the sort stage's M read-back."""
+    cache = getattr(_pinned, "cache", None)
+    if cache is None:
+        cache = _pinned.cache = {}
+    key = torch.device(device).index
+    if key not in cache:
+        cache[key] = torch.zeros(1, dtype=torch.int64).pin_memory()
+    return cache[key]
+
+
+_sm_count = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _sm_count:
+        _sm_count[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _sm_count[idx]

@@ -1,0 +1,567 @@
+// msplat_b200/csrc/blend.cu -- tile-based alpha blending, forward and backward.
+//
+// Replaces alphaBlendingForward/Backward and their channel-chunk dispatcher
+//   /root/reference/msplat/src/alpha_blending.cu:16-110 (K11), :112-246 (K12), :248-573 (D1).
+// Per-pixel semantics are exactly those of the reference: front-to-back over the
+// tile's depth-sorted list, skip on power > 0 / alpha < 1/255, terminate before the entry that
+// would push T below 1e-4, out = F + T*bg; backward replays T back-to-front from final_T and
+// ncontrib.
+//
+// Design (one CTA of 256 threads per 16x16 tile, like the reference, but):
+//  * a pack pass turns the per-Gaussian inputs into one 32-byte record
+//      {u, v, conic.x, conic.y | conic.z, opacity, hx, hy}
+//    plus a 16-byte-aligned feature row, so a batch of 256 list entries is staged into shared
+//    memory with 16-byte cp.async (LDGSTS) copies, double-buffered against the blend loop;
+//  * each warp owns an 8x4 pixel block; lane l tests staged Gaussian 32k+l against the warp's
+//    block (conservative alpha-footprint box hx, hy, blend_math.cuh) and a ballot yields the
+//    Gaussians worth visiting -- most of a tile's list never touches a given 8x4 block, so the
+//    per-pair work drops by ~3-4x without changing any pixel's result;
+//  * warp-vote early termination (a warp stops when its 32 pixels are done, the CTA when all are);
+//  * features live in shared memory (the reference re-reads them from global per pair);
+//  * backward: per-Gaussian gradients are reduced across the warp with a transposing butterfly
+//    (12 shuffles for 10 values instead of 50) and leave the SM as ONE red.global per value per
+//    warp, into a packed 32-byte gradient record; the reference issues (6+C) atomics per lane;
+//  * the backward walks only list positions below the tile's max ncontrib.
+#include "blend_math.cuh"
+
+namespace msb {
+
+constexpr int BL_NT = 256;
+constexpr int BL_BATCH = 256;
+
+// ------------------------------------------------------------------------------------------------
+// pack / unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blend_pack_kernel(int P, int C, int Cpad, const float2* __restrict__ uv,
+                                                         const float* __restrict__ conic,
+                                                         const float* __restrict__ opacity,
+                                                         const float* __restrict__ feature,
+                                                         float4* __restrict__ rec, float* __restrict__ featp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float2 p = uv[i];
+    const float cx = conic[3 * i], cy = conic[3 * i + 1], cz = conic[3 * i + 2];
+    const float op = opacity[i];
+    float hx, hy;
+    cull_extent(cx, cy, cz, op, hx, hy);
+    rec[2 * i] = make_float4(p.x, p.y, cx, cy);
+    rec[2 * i + 1] = make_float4(cz, op, hx, hy);
+    if (featp != nullptr) {
+        for (int k = 0; k < Cpad; ++k) featp[i * Cpad + k] = k < C ? feature[i * C + k] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) blend_unpack_kernel(int P, int C, int Cpad, const float* __restrict__ grec,
+                                                           const float* __restrict__ gfeat,
+                                                           float* __restrict__ dL_duv,
+                                                           float* __restrict__ dL_dconic,
+                                                           float* __restrict__ dL_dopacity,
+                                                           float* __restrict__ dL_dfeature) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 a = reinterpret_cast<const float4*>(grec)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(grec)[2 * i + 1];
+    dL_duv[2 * i] = a.x;
+    dL_duv[2 * i + 1] = a.y;
+    dL_dconic[3 * i] = a.z;
+    dL_dconic[3 * i + 1] = a.w;
+    dL_dconic[3 * i + 2] = b.x;
+    dL_dopacity[i] = b.y;
+    if (dL_dfeature != nullptr)
+        for (int k = 0; k < C; ++k) dL_dfeature[i * C + k] = gfeat[i * Cpad + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory stage: 256 records + 256 feature rows
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+struct Stage {
+    float4 rec[BL_BATCH * 2];
+    float feat[BL_BATCH * CH];
+};
+
+template <int CH>
+__device__ __forceinline__ void stage_issue(Stage<CH>& st, int slot, int id, const float4* __restrict__ rec,
+                                            const float* __restrict__ featp, int fstride, int foff) {
+    const float4* r = rec + 2 * (long long)id;
+    cp_async16(&st.rec[2 * slot], r);
+    cp_async16(&st.rec[2 * slot + 1], r + 1);
+    const float* f = featp + (long long)id * fstride + foff;
+#pragma unroll
+    for (int k = 0; k < CH; k += 4) cp_async16(&st.feat[slot * CH + k], f + k);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
+                                                          const float* __restrict__ featp, int fstride, int foff,
+                                                          const int* __restrict__ ids,
+                                                          const int2* __restrict__ tile_range, float bg,
+                                                          int c_valid, int W, int H, int write_aux,
+                                                          float* __restrict__ final_T, int* __restrict__ ncontrib,
+                                                          float* __restrict__ image) {
+    extern __shared__ __align__(16) unsigned char bl_raw[];
+    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
+    const int tile = blockIdx.y * gxt + blockIdx.x;
+    // warp -> 8x4 pixel block of the 16x16 tile
+    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const bool inside = px < W && py < H;
+    bool done = !inside;
+
+    const int2 range = tile_range[tile];
+    const int n = range.y - range.x;
+    const int nb = (n + BL_BATCH - 1) / BL_BATCH;
+
+    float T = 1.0f;
+    int last = 0;
+    float F[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) F[k] = 0.f;
+
+    // prologue: stage batch 0, prefetch the id of batch 1
+    int id_next = 0;
+    if (nb > 0) {
+        if (tid < n) stage_issue<CH>(stages[0], tid, ids[range.x + tid], rec, featp, fstride, foff);
+        cp_async_commit();
+        if (BL_BATCH + tid < n) id_next = ids[range.x + BL_BATCH + tid];
+    }
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<0>();
+        // barrier: batch b is visible to everyone, everyone is done with batch b-1; also the vote
+        if (__syncthreads_and(done)) break;
+        if (b + 1 < nb) {
+            if ((b + 1) * BL_BATCH + tid < n)
+                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            cp_async_commit();
+            if ((b + 2) * BL_BATCH + tid < n) id_next = ids[range.x + (b + 2) * BL_BATCH + tid];
+        }
+        const Stage<CH>& st = stages[b & 1];
+        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        const int base = b * BL_BATCH;
+        if (__all_sync(0xffffffffu, done)) continue;  // this warp's 32 pixels are finished
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            // lane-parallel footprint test of 32 staged Gaussians against this warp's 8x4 block
+            bool hit = false;
+            if (k0 + lane < cnt) {
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
+                                  (r0.y - r1.w > wy1);
+                hit = !miss;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 r0 = st.rec[2 * j];      // u, v, cx, cy   (broadcast LDS.128)
+                const float4 r1 = st.rec[2 * j + 1];  // cz, opacity, hx, hy
+                if (!done) {
+                    const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
+                    const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
+                    float G, alpha;
+                    if (pair_alpha(power, r1.y, G, alpha)) {
+                        const float nT = fmul(T, fadd(-alpha, 1.0f));
+                        if (nT < kTmin) {
+                            done = true;  // alpha_blending.cu:90-94: entry not blended
+                        } else {
+                            const float* f = &st.feat[j * CH];
+#pragma unroll
+                            for (int k = 0; k < CH; k += 4) {
+                                const float4 fv = *reinterpret_cast<const float4*>(f + k);
+                                F[k] = ffma(T, fmul(alpha, fv.x), F[k]);
+                                F[k + 1] = ffma(T, fmul(alpha, fv.y), F[k + 1]);
+                                F[k + 2] = ffma(T, fmul(alpha, fv.z), F[k + 2]);
+                                F[k + 3] = ffma(T, fmul(alpha, fv.w), F[k + 3]);
+                            }
+                            T = nT;
+                            last = base + j + 1;
+                        }
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    cp_async_wait<0>();
+    if (inside) {
+        const long long pix = (long long)py * W + px;
+        if (write_aux) {
+            final_T[pix] = T;
+            ncontrib[pix] = last;
+        }
+        const long long hw = (long long)H * W;
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// Transposing butterfly: N per-lane values -> after 5 steps lane L holds, in v[0], the warp-wide
+// sum of ONE of the N values (which one: red_slot()).  ceil(N/2)+ceil(N/4)+... shuffles.
+template <int N, int OFF>
+struct WarpRed {
+    static __device__ __forceinline__ void run(float* v, bool const* upper) {
+        constexpr int Hn = (N + 1) / 2;
+        const bool up = upper[0];
+#pragma unroll
+        for (int i = 0; i < Hn; ++i) {
+            const float a = v[i];
+            const float b = (i + Hn < N) ? v[i + Hn] : 0.f;
+            const float send = up ? a : b;
+            const float keep = up ? b : a;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        WarpRed<Hn, OFF / 2>::run(v, upper + 1);
+    }
+};
+template <int N>
+struct WarpRed<N, 0> {
+    static __device__ __forceinline__ void run(float*, bool const*) {}
+};
+
+// which of the N values ends up in lane `lane` (or -1 if that lane holds nothing)
+template <int N>
+__device__ __forceinline__ int red_slot(int lane) {
+    int n[6];
+    n[0] = N;
+    for (int s = 0; s < 5; ++s) n[s + 1] = (n[s] + 1) / 2;
+    int p = 0;
+    bool ok = true;
+    for (int s = 4; s >= 0; --s) {  // unwind from the last step (offset 1) to the first (offset 16)
+        const int off = 16 >> s;
+        const int Hn = n[s + 1];
+        if (lane & off) {
+            if (p + Hn >= n[s]) ok = false;
+            p += Hn;
+        }
+    }
+    return ok ? p : -1;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+                                                          const float* __restrict__ featp, int fstride, int foff,
+                                                          const int* __restrict__ ids,
+                                                          const int2* __restrict__ tile_range, float bg,
+                                                          int c_valid, int W, int H,
+                                                          const float* __restrict__ final_T,
+                                                          const int* __restrict__ ncontrib,
+                                                          const float* __restrict__ dL_dimage,
+                                                          float* __restrict__ grec, float* __restrict__ gfeat,
+                                                          int geom_grads) {
+    constexpr int NV = 6 + CH;
+    extern __shared__ __align__(16) unsigned char bl_raw[];
+    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
+    __shared__ int s_id[2][BL_BATCH];
+    __shared__ int s_max[BL_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
+    const int tile = blockIdx.y * gxt + blockIdx.x;
+    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const bool inside = px < W && py < H;
+    const long long pix = (long long)py * W + px;
+    const long long hw = (long long)H * W;
+
+    const int2 range = tile_range[tile];
+    const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
+    // tile-wide max -> only list positions [0, maxc) are ever needed
+    int wmax = lc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    int maxc = 0;
+#pragma unroll
+    for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
+    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
+
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    float dpix[CH], accum[CH], lastf[CH];
+    float bgdot = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
+        accum[k] = 0.f;
+        lastf[k] = 0.f;
+        bgdot = fmaf(bg, dpix[k], bgdot);
+    }
+    float last_alpha = 0.f;
+
+    // this lane's role after the transposing reduction
+    const int slot = red_slot<NV>(lane);
+    bool upper[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) upper[s] = (lane & (16 >> s)) != 0;
+    float* gptr = nullptr;   // base of this lane's gradient component
+    int gstride = 0;
+    if (slot >= 0 && slot < 6) {
+        if (geom_grads) { gptr = grec + slot; gstride = 8; }
+    } else if (slot >= 6 && slot - 6 < c_valid) {
+        gptr = gfeat + foff + (slot - 6);
+        gstride = fstride;
+    }
+
+    // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
+    int id_next = 0;
+    if (nb > 0) {
+        if (tid < maxc) {
+            const int id = ids[range.x + maxc - 1 - tid];
+            s_id[0][tid] = id;
+            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
+        }
+        cp_async_commit();
+        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
+    }
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (b + 1 < nb) {
+            if ((b + 1) * BL_BATCH + tid < maxc) {
+                s_id[(b + 1) & 1][tid] = id_next;
+                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            }
+            cp_async_commit();
+            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
+        }
+        const Stage<CH>& st = stages[b & 1];
+        const int* sid = s_id[b & 1];
+        const int cnt = min(BL_BATCH, maxc - b * BL_BATCH);
+        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
+        if (pos0 - (cnt - 1) >= wmax) continue;    // whole batch lies beyond every pixel of this warp
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            bool hit = false;
+            if (k0 + lane < cnt) {
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
+                                  (r0.y - r1.w > wy1);
+                hit = !miss && (pos0 - (k0 + lane) < wmax);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 r0 = st.rec[2 * j];
+                const float4 r1 = st.rec[2 * j + 1];
+                const int pos = pos0 - j;
+                float v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v[i] = 0.f;
+                bool valid = false;
+                if (pos < lc) {  // alpha_blending.cu:185-187
+                    const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
+                    const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
+                    float G, alpha;
+                    if (pair_alpha(power, r1.y, G, alpha)) {
+                        valid = true;
+                        const float rinv = rcp_approx(1.0f - alpha);
+                        T = T * rinv;  // :205
+                        const float wgt = alpha * T;
+                        const float om = 1.0f - last_alpha;
+                        float dL_dalpha = 0.f;
+                        const float* f = &st.feat[j * CH];
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) {
+                            const float fk = f[k];
+                            accum[k] = fmaf(lastf[k], last_alpha, om * accum[k]);  // :213-214
+                            lastf[k] = fk;
+                            dL_dalpha = fmaf(fk - accum[k], dpix[k], dL_dalpha);   // :217
+                            v[6 + k] = wgt * dpix[k];                              // :218-219
+                        }
+                        dL_dalpha = fmaf(dL_dalpha, T, (-T_final * rinv) * bgdot);  // :222-229
+                        last_alpha = alpha;
+                        const float dL_dG = r1.y * dL_dalpha;  // :231
+                        const float gdl = G * dL_dG;
+                        v[0] = gdl * (-dx * r0.z - dy * r0.w);  // :232-237
+                        v[1] = gdl * (-dy * r1.x - dx * r0.w);
+                        v[2] = -0.5f * gdl * dx * dx;            // :238-242
+                        v[3] = -gdl * dx * dy;
+                        v[4] = -0.5f * gdl * dy * dy;
+                        v[5] = G * dL_dalpha;                    // :243
+                    }
+                }
+                if (__any_sync(0xffffffffu, valid)) {
+                    WarpRed<NV, 16>::run(v, upper);
+                    if (gptr != nullptr && v[0] != 0.f) atomicAdd(gptr + (long long)sid[j] * gstride, v[0]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+static inline int pick_fwd_ch(int rem) { return rem >= 32 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4; }
+static inline int pick_bwd_ch(int rem) { return rem >= 16 ? 16 : rem > 4 ? 8 : 4; }
+
+template <int CH>
+static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
+                      const int* ids, const int2* tr, float bg, int c_valid, int W, int H, int write_aux,
+                      float* final_T, int* ncontrib, float* image) {
+    const size_t smem = 2 * sizeof(Stage<CH>);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_fwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_fwd: cudaFuncSetAttribute failed");
+    }
+    blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
+                                                    final_T, ncontrib, image);
+    return check_launch("alpha_blending_fwd");
+}
+
+template <int CH>
+static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
+                      const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
+                      const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
+    const size_t smem = 2 * sizeof(Stage<CH>);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    }
+    blend_bwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
+                                                    ncontrib, dL_dimage, grec, gfeat, geom);
+    return check_launch("alpha_blending_bwd");
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+// Padded feature-row width used by the packed layout.
+int msb_blend_cpad(int C) { return C <= 4 ? 4 : C <= 8 ? 8 : (C + 15) / 16 * 16; }
+
+// Workspace: rec [P][8] floats, then (if C != Cpad) featp [P][Cpad] floats.
+size_t msb_blend_fwd_workspace_bytes(int P, int C) {
+    const int Cpad = msb_blend_cpad(C);
+    size_t b = (size_t)P * 8 * sizeof(float);
+    if (C != Cpad) b += (size_t)P * Cpad * sizeof(float);
+    return b + 256;
+}
+
+// Backward workspace: grec [P][8] + gfeat [P][Cpad] (zeroed by the call).
+size_t msb_blend_bwd_workspace_bytes(int P, int C) {
+    return (size_t)P * (8 + msb_blend_cpad(C)) * sizeof(float) + 256;
+}
+
+// Forward.  packed (workspace, msb_blend_fwd_workspace_bytes) is an OUTPUT that the backward
+// pass reuses (the caller keeps it alive with the autograd context).
+int msb_alpha_blending_fwd(const float* uv, const float* conic, const float* opacity, const float* feature,
+                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int P, int C, int W,
+                           int H, float* image, float* final_T, int32_t* ncontrib, void* packed,
+                           size_t packed_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || C < 0 || W <= 0 || H <= 0 || !tile_range || !final_T || !ncontrib)
+        return set_error(MSB_ERR_ARG, "alpha_blending_fwd: bad argument");
+    if (C > 0 && !image) return set_error(MSB_ERR_ARG, "alpha_blending_fwd: null image");
+    if (P > 0 && (!uv || !conic || !opacity || !packed || (C > 0 && !feature)))
+        return set_error(MSB_ERR_ARG, "alpha_blending_fwd: null pointer");
+    if (packed_bytes < msb_blend_fwd_workspace_bytes(P, C))
+        return set_error(MSB_ERR_WORKSPACE, "alpha_blending_fwd: workspace too small");
+    const int Cpad = msb_blend_cpad(C);
+    float4* rec = reinterpret_cast<float4*>(packed);
+    float* featp = (C != Cpad) ? reinterpret_cast<float*>(packed) + (size_t)P * 8 : nullptr;
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) || (C == Cpad && (reinterpret_cast<uintptr_t>(feature) & 15u)))
+        return set_error(MSB_ERR_ARG, "alpha_blending_fwd: 16-byte alignment");
+    if (P > 0) {
+        blend_pack_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, C, Cpad, reinterpret_cast<const float2*>(uv),
+                                                                      conic, opacity, feature, rec, featp);
+        int rc = check_launch("alpha_blending_fwd/pack");
+        if (rc) return rc;
+    }
+    const float* fsrc = (C != Cpad) ? featp : feature;
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+    const int2* tr = reinterpret_cast<const int2*>(tile_range);
+    int c0 = 0, first = 1;
+    do {  // at least one pass so that final_T / ncontrib exist even for C == 0
+        const int rem = Cpad - c0;
+        const int ch = C == 0 ? 4 : pick_fwd_ch(rem);
+        const int c_valid = max(0, min(ch, C - c0));
+        float* img = image ? image + (size_t)c0 * H * W : nullptr;
+        int rc;
+        if (C == 0) {  // geometry-only pass: stage rec twice (no feature rows exist)
+            rc = launch_fwd<4>(grid, st, rec, reinterpret_cast<const float*>(rec), 8, 0, idx_sorted, tr, bg, 0, W, H, 1,
+                               final_T, ncontrib, img);
+        } else if (ch == 32) {
+            rc = launch_fwd<32>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                                ncontrib, img);
+        } else if (ch == 16) {
+            rc = launch_fwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                                ncontrib, img);
+        } else if (ch == 8) {
+            rc = launch_fwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                               ncontrib, img);
+        } else {
+            rc = launch_fwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                               ncontrib, img);
+        }
+        if (rc) return rc;
+        c0 += ch;
+        first = 0;
+    } while (c0 < C);
+    return MSB_OK;
+}
+
+// Backward.  `packed` is the buffer produced by the forward call on the same inputs.
+int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, const int32_t* tile_range, float bg,
+                           int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
+                           const float* dL_dimage, const void* packed, float* dL_duv, float* dL_dconic,
+                           float* dL_dopacity, float* dL_dfeature, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || C < 0 || W <= 0 || H <= 0) return set_error(MSB_ERR_ARG, "alpha_blending_bwd: bad argument");
+    if (P == 0) return MSB_OK;
+    if (!tile_range || !final_T || !ncontrib || !packed || !dL_duv || !dL_dconic || !dL_dopacity || !ws ||
+        (C > 0 && (!dL_dimage || !dL_dfeature || !feature)))
+        return set_error(MSB_ERR_ARG, "alpha_blending_bwd: null pointer");
+    if (ws_bytes < msb_blend_bwd_workspace_bytes(P, C))
+        return set_error(MSB_ERR_WORKSPACE, "alpha_blending_bwd: workspace too small");
+    const int Cpad = msb_blend_cpad(C);
+    const float4* rec = reinterpret_cast<const float4*>(packed);
+    const float* fsrc = (C != Cpad) ? reinterpret_cast<const float*>(packed) + (size_t)P * 8 : feature;
+    float* grec = reinterpret_cast<float*>(ws);
+    float* gfeat = grec + (size_t)P * 8;
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)P * (8 + Cpad) * sizeof(float), st);
+    if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: memset failed");
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+    const int2* tr = reinterpret_cast<const int2*>(tile_range);
+    for (int c0 = 0; c0 < C;) {
+        const int rem = Cpad - c0;
+        const int ch = pick_bwd_ch(rem);
+        const int c_valid = min(ch, C - c0);
+        const float* dimg = dL_dimage + (size_t)c0 * H * W;
+        int rc;
+        // geometric gradients are linear in the channels: every chunk adds its share (D1 in the
+        // reference does the same, alpha_blending.cu:436-567)
+        if (ch == 16)
+            rc = launch_bwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                                dimg, grec, gfeat, 1);
+        else if (ch == 8)
+            rc = launch_bwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                               dimg, grec, gfeat, 1);
+        else
+            rc = launch_bwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                               dimg, grec, gfeat, 1);
+        if (rc) return rc;
+        c0 += ch;
+    }
+    blend_unpack_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, C, Cpad, grec, gfeat, dL_duv, dL_dconic,
+                                                                    dL_dopacity, dL_dfeature);
+    return check_launch("alpha_blending_bwd/unpack");
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// msplat_b200/csrc/common.cuh -- shared device helpers for the sm_100a kernels.
+//
+// Numerics policy.  The library is compiled WITHOUT --use_fast_math but with -ftz=true.
+// Stages whose outputs feed integer decisions that must be bit-identical to the reference
+// (uv/depth -> sort keys, cov3d -> radius/tiles, blend power/alpha -> skip/terminate tests)
+// are written with explicit round-to-nearest intrinsics (__fmul_rn/__fmaf_rn/__fadd_rn are
+// never contracted or re-associated by nvcc) and explicit MUFU approximations, in the exact
+// operation order the reference's `-O3 --use_fast_math` sm_100 build executes (SASS dataflow
+// recorded in DESIGN.md "Numerics mirrored from the reference build").  Everything else is
+// ordinary FP32 with FMA contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MSB_TILE 16          // reference: msplat/include/config.h:7-8 (BLOCK_X = BLOCK_Y = 16)
+#define MSB_TILE_PIX 256
+
+namespace msb {
+
+// ---- host/device portability ---------------------------------------------------------------
+// The per-Gaussian math headers (geom.cuh, sh_eval.cuh, blend_math.cuh) also compile for the
+// host so that tools/host_check.cu can exercise exactly the same source on a CPU-only box
+// (the -m "not gpu" tests).  On the host the MUFU approximations become IEEE operations, so
+// host results are tolerance-level, not bit-level, checks.
+#define MSB_HD __host__ __device__ __forceinline__
+
+#ifdef __CUDA_ARCH__
+// explicit round-to-nearest ops: never contracted / re-associated by nvcc
+MSB_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+MSB_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+MSB_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+MSB_HD int f2i_rz(float x) { return __float2int_rz(x); }
+MSB_HD int f2i_ru(float x) { return __float2int_ru(x); }
+MSB_HD float ldg_f(const float* p) { return __ldg(p); }
+// MUFU approximations (what --use_fast_math lowers `/`, sqrtf, expf to)
+MSB_HD float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+MSB_HD float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+MSB_HD float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// max/min with the FMNMX NaN rule (returns the non-NaN operand)
+MSB_HD float fmax_ftz(float a, float b) {
+    float y;
+    asm("max.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+    return y;
+}
+MSB_HD float fmin_ftz(float a, float b) {
+    float y;
+    asm("min.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
+    return y;
+}
+#else
+}  // namespace msb
+#include <math.h>
+namespace msb {
+MSB_HD float fmul(float a, float b) { volatile float r = a * b; return r; }
+MSB_HD float fadd(float a, float b) { volatile float r = a + b; return r; }
+MSB_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+MSB_HD int f2i_sat(double x) {
+    if (x != x) return 0;
+    if (x >= 2147483647.0) return 2147483647;
+    if (x <= -2147483648.0) return (int)(-2147483647 - 1);
+    return (int)x;
+}
+MSB_HD int f2i_rz(float x) { return f2i_sat(trunc((double)x)); }
+MSB_HD int f2i_ru(float x) { return f2i_sat(ceil((double)x)); }
+MSB_HD float ldg_f(const float* p) { return *p; }
+MSB_HD float rcp_approx(float x) { return 1.0f / x; }
+MSB_HD float sqrt_approx(float x) { return sqrtf(x); }
+MSB_HD float ex2_approx(float x) { return exp2f(x); }
+MSB_HD float fmax_ftz(float a, float b) { return fmaxf(a, b); }
+MSB_HD float fmin_ftz(float a, float b) { return fminf(a, b); }
+#endif
+MSB_HD int imin(int a, int b) { return a < b ? a : b; }
+MSB_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ---- streaming global access ------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// ---- cp.async (LDGSTS) ------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- block-cooperative AoS slab staging ----------------------------------------------------
+// A block owns rows [row0, row0+rows) of a row-major [P, K] float array.  The block's slab
+// is contiguous in memory, so it is moved with fully coalesced 16-byte accesses (scalar for
+// the <4-float tail of the last block) into shared memory, where each thread then reads its
+// own row with stride K (conflict-free for odd K; rows with even K are read as vectors).
+// This is the "vectorised 16-byte loads" path for the [P,2]/[P,3]/[P,4]/[P,6] tensors of
+// the msplat API.  Requires g + first to be 16-byte aligned (base pointers are checked by
+// the C-ABI entry points; first = blockIdx * 256 * K is a multiple of 4).
+template <int NT>
+__device__ __forceinline__ void slab_load(float* __restrict__ smem, const float* __restrict__ g,
+                                          long long first, int count) {
+    const float* src = g + first;
+    const int nvec = count >> 2;
+    const float4* v = reinterpret_cast<const float4*>(src);
+    float4* d = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < nvec; i += NT) d[i] = ldg_stream4(v + i);
+    for (int i = 4 * nvec + threadIdx.x; i < count; i += NT) smem[i] = __ldg(src + i);
+}
+
+template <int NT>
+__device__ __forceinline__ void slab_store(float* __restrict__ g, const float* __restrict__ smem,
+                                           long long first, int count) {
+    float* dst = g + first;
+    const int nvec = count >> 2;
+    float4* v = reinterpret_cast<float4*>(dst);
+    const float4* s = reinterpret_cast<const float4*>(smem);
+    for (int i = threadIdx.x; i < nvec; i += NT) v[i] = s[i];
+    for (int i = 4 * nvec + threadIdx.x; i < count; i += NT) dst[i] = smem[i];
+}
+
+// ---- warp helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+}  // namespace msb
+
+// ---- host-side error plumbing (defined in capi.cu) ------------------------------------------
+extern "C" const char* msb_last_error(void);
+namespace msb {
+int set_error(int code, const char* msg);
+int check_launch(const char* what);
+}  // namespace msb
+
+#define MSB_OK 0
+#define MSB_ERR_ARG (-1)
+#define MSB_ERR_WORKSPACE (-2)
+#define MSB_ERR_RANGE (-3)

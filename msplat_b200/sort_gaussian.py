@@ -1,0 +1,48 @@
+"""sort_gaussian: duplicate Gaussians per touched tile, sort by [tile | depth], tile ranges.
+
+Reference: /root/reference/msplat/sort_gaussian.py:8-54 (cumsum -> compute_gaussian_key ->
+torch.sort -> gather -> compute_tile_gaussian_range), src/sort_gaussian.cu:17-142 (K9/K10).
+Outputs are bit-exact with the reference: idx_sorted int32 [M], tile_range int32 [T,2].
+Not differentiable (like the reference).
+"""
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import as_f32, as_i32, check, ptr, stream_ptr
+
+
+def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, tiles: Tensor) -> Tuple[Tensor, Tensor]:
+    """uv [P,2], depth [P,1], radius/tiles int32 [P] or [P,1] -> (idx_sorted [M], tile_range [T,2])."""
+    with torch.no_grad():
+        u, d = as_f32(uv, "uv"), as_f32(depth, "depth")
+        r, t = as_i32(radius, "radius"), as_i32(tiles, "tiles")
+        P = u.shape[0]
+        if u.shape != (P, 2) or d.numel() != P or r.numel() != P or t.numel() != P:
+            raise RuntimeError("uv must be [P,2]; depth, radius, tiles must have P elements")
+        dev = u.device
+        L = _lib.lib()
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        tile_range = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            offsets = torch.empty((P,), dtype=torch.int32, device=dev)
+            ws1 = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
+            total = _lib.pinned_i64(dev)
+            check(L.msb_sort_scan(ptr(t), P, ptr(offsets), ptr(total), ptr(ws1), ws1.numel(), st), "sort_scan")
+            _lib.count_launches(3 if P else 0)
+            # the one host<->device sync of the pipeline: M sizes the output (reference: two .item())
+            torch.cuda.current_stream(dev).synchronize()
+            M = int(total[0])
+            if M >= 2 ** 30:
+                raise RuntimeError(f"sort_gaussian: {M} tile intersections exceed the supported 2^30")
+            idx_sorted = torch.empty((M,), dtype=torch.int32, device=dev)
+            ws2 = torch.empty((L.msb_sort_workspace_bytes(M, int(W), int(H)),), dtype=torch.uint8, device=dev)
+            check(L.msb_sort_gaussian(ptr(u), ptr(d), ptr(r), ptr(t), ptr(offsets), P, M, int(W), int(H),
+                                      ptr(idx_sorted), ptr(tile_range), ptr(ws2), ws2.numel(), _lib.sm_count(dev), st),
+                  "sort_gaussian")
+            if M > 0 and P > 0:
+                _lib.count_launches(2 + L.msb_sort_num_passes(int(W), int(H)))
+    return idx_sorted, tile_range
