@@ -1,0 +1,423 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: fwd+bwd renders/s @ 3M Gaussians, 1920x1080, SH degree 3,
+RGB+depth (BASELINE.json configs[2], SURVEY 8d "Config #3").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|oracle]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One STEP = `views` (default 4) fwd+bwd renders of the same resident 3M-Gaussian cloud from
+different cameras through the public steps API
+    project_point -> compute_sh(+0.5, clamp) -> cat(rgb, depth) -> compute_cov3d -> ewa_project
+    -> sort_gaussian -> alpha_blending -> (image * G).sum().backward()
+with gradients to xyz, scale, rotation, opacity and SH coefficients accumulated in one flat
+buffer.  With N > 1 every rank renders its own `views` cameras (weak scaling) and the flat
+gradients are sum-all-reduced once per step (NCCL).  value = N * views / step_time.
+
+--impl ours       msplat_b200 (default)
+--impl reference  the UNMODIFIED reference CUDA build from baseline/_ref through its own public
+                  API on the same tensors/config (the comparator the north star names); if that
+                  build is absent, the CPU oracle port on a bounded sample (rank 0 only)
+--impl oracle     the CPU oracle port on a bounded sample (what `cpu_baseline` reports)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "fwd+bwd renders/s @3M Gaussians 1080p SH3"
+P_FULL, W_FULL, H_FULL, SH_DEG, SIGMA = 3_000_000, 1920, 1080, 3, 2.0
+
+
+# ------------------------------------------------------------------------------------------------
+# the workload (identical code for our library and for the reference build)
+# ------------------------------------------------------------------------------------------------
+def render_once(api, params, cam, W, H, G):
+    xyz, scale, quat, opacity, shs = params
+    intr, extr, center = cam
+    uv, depth = api.project_point(xyz, intr, extr, W, H)
+    visible = depth != 0
+    dirs = xyz - center
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    rgb = torch.clamp_min(api.compute_sh(shs, dirs, visible.squeeze(-1)) + 0.5, 0.0)
+    feature = torch.cat([rgb, depth], dim=-1)
+    cov3d = api.compute_cov3d(scale, quat, visible)
+    conic, radius, tiles = api.ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible)
+    ids, tile_range = api.sort_gaussian(uv, depth, W, H, radius, tiles)
+    image = api.alpha_blending(uv, conic, opacity, feature, ids, tile_range, 0.0, W, H)
+    loss = (image * G).sum()
+    loss.backward()
+    return loss.detach()
+
+
+def make_cameras(scene, n, device):
+    from msplat_b200.scenes import orbit_cameras
+    cams = []
+    for extr in orbit_cameras(max(n, 2), yaw_deg=20.0, shift=1.0)[:n]:
+        R, t = extr[:3, :3], extr[:3, 3]
+        center = -(R.T @ t)
+        cams.append((scene.intr.detach().cpu().clone(), extr.clone(), center.clone()))
+    return cams
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def physical_gpu_index(local):
+    cvd = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [x for x in cvd.split(",") if x.strip()]
+    if ids and local < len(ids) and ids[local].strip().isdigit():
+        return int(ids[local])
+    return local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic HBM bytes per unit of each C-ABI call at SH3 RGB + depth (DESIGN.md "Kernels")
+def algorithmic_bytes(name, P, M, Cs, D, C):
+    T = {
+        "project_point_forward": P * (12 + 12),
+        "project_point_backward": P * (12 + 4 + 12 + 12),
+        "compute_cov3d_forward": P * (12 + 16 + 1 + 24),
+        "compute_cov3d_backward": P * (12 + 16 + 1 + 24 + 28),
+        "ewa_project_forward": P * (12 + 24 + 8 + 1 + 12 + 8),
+        "ewa_project_backward": P * (12 + 24 + 4 + 12 + 12 + 24),
+        "compute_sh_forward": P * (4 * Cs * D + 12 + 1 + 4 * Cs),
+        "compute_sh_backward": P * (2 * 4 * Cs * D + 12 + 1 + 4 * Cs + 12),
+        "sort_scan": P * (4 + 4 + 4),
+        "sort_gaussian": P * 20 + M * (12 + 24 * 6 + 8),
+    }
+    return T.get(name)
+
+
+def barrier_sync(world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_gpu(args, api, impl):
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    from msplat_b200.parallel import FlatGrads
+    from msplat_b200.scenes import frustum_scene
+
+    P, W, H = args.gaussians, args.width, args.height
+    scene = frustum_scene(P, W, H, SIGMA, seed=0, sh_degree=SH_DEG).to(dev)
+    params = [t.clone().requires_grad_() for t in (scene.xyz, scene.scale, scene.quat, scene.opacity, scene.shs)]
+    grads = FlatGrads(params)
+    V = args.views
+    cams_host = make_cameras(scene, V * world, "cpu")[rank * V:(rank + 1) * V]
+    cams = [tuple(t.to(dev) for t in c) for c in cams_host]
+    C = 4
+    G_host = torch.randn(C, H, W, generator=torch.Generator().manual_seed(1)).pin_memory()
+    G = G_host.to(dev)
+
+    def step(cams_, G_):
+        grads.zero_()
+        total = None
+        for cam in cams_:
+            l = render_once(api, params, cam, W, H, G_)
+            total = l if total is None else total + l
+        grads.all_reduce()
+        return total
+
+    for _ in range(args.warmup):
+        step(cams, G)
+    ours = impl == "ours"
+    if ours:
+        from msplat_b200 import _lib
+    # ---------------- timed region: inputs resident in HBM ----------------
+    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    barrier_sync(world)
+    if ours:
+        _lib.reset_launches()
+        _lib.TIMING = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(cams, G)
+    e1.record()
+    barrier_sync(world)
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launches() if ours else None
+    timing = _lib.TIMING if ours else None
+    if ours:
+        _lib.TIMING = None
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    ms_per_step = ms / args.steps
+    value = world * V * args.steps / (ms / 1e3)
+
+    # ---------------- e2e: per step H2D of the step's inputs (cameras + cotangent), D2H of the loss ----------
+    cam_pinned = [tuple(t.pin_memory() for t in c) for c in cams_host]
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    h2d = sum(sum(t.numel() * 4 for t in c) for c in cam_pinned) + G_host.numel() * 4
+    barrier_sync(world)
+    e0.record()
+    for _ in range(args.steps):
+        cams_e = [tuple(t.to(dev, non_blocking=True) for t in c) for c in cam_pinned]
+        G_e = G_host.to(dev, non_blocking=True)
+        tot = step(cams_e, G_e)
+        loss_host.copy_(tot.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+    e1.record()
+    barrier_sync(world)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * V * args.steps / (float(t[0]) / 1e3)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "renders/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"S-frustum(P={P}, {W}x{H}, sigma_med={SIGMA}, seed=0), SH degree {SH_DEG}, "
+                               f"RGB+depth (C=4), fwd+bwd, {V} views per rank per step, grads to xyz/scale/rot/"
+                               f"opacity/shs" + (", one NCCL sum all-reduce of the flat grads per step" if world > 1 else ""),
+                   "gaussians": P, "width": W, "height": H, "sh_degree": SH_DEG, "channels": C,
+                   "views_per_rank_per_step": V, "parallelism": f"view-dp{world}",
+                   "cache": "inputs (~0.7 GB of parameters per render) exceed the 126 MB L2; no explicit flush"},
+        "impl": impl, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "renders/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+    }
+    if ours:
+        out["gpu_launches"] = launches
+        out.update(stage_report(timing, args, api, params, cams[0], G, clocks))
+    else:
+        out["gpu_launches"] = 0
+        out["cpu_baseline"] = {"value": value, "unit": "renders/s", "cores": 0, "kind": "reference-cuda",
+                               "sample": "full workload on the GPU through the unmodified reference build "
+                                         "(baseline/_ref); no CPU implementation exists in the reference"}
+    if rank == 0:
+        if ours and world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_report(timing, args, api, params, cam, G, clocks):
+    """Per-C-ABI-call durations (CUDA events recorded on the launching stream inside the timed
+    region) -> roofline of the dominant call + a per-stage table."""
+    from msplat_b200 import _lib
+    P, W, H = args.gaussians, args.width, args.height
+    Cs, D, C = 3, (SH_DEG + 1) ** 2, 4
+    agg = {}
+    for name, a, b in timing:
+        d = agg.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+    # pairs = sum(ncontrib) and M for one representative view
+    with torch.no_grad():
+        xyz, scale, quat, opacity, shs = [p.detach() for p in params]
+        intr, extr, center = cam
+        uv, depth = api.project_point(xyz, intr, extr, W, H)
+        vis = depth != 0
+        cov = api.compute_cov3d(scale, quat, vis)
+        conic, radius, tiles = api.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+        ids, tr = api.sort_gaussian(uv, depth, W, H, radius, tiles)
+        from msplat_b200.alpha_blending import _blend_forward
+        feat = torch.rand(P, C, device=xyz.device)
+        _, _, ncontrib, _ = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
+        pairs = int(ncontrib.sum())
+        M = int(ids.numel())
+    hbm, sm_max, src = measured_peaks()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    f_hz = (clocks["sm_mhz"] if clocks else sm_max) * 1e6
+    total_ms = sum(v[0] for v in agg.values())
+    stages = {}
+    for name, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        ms = tot / n
+        st = {"ms": round(ms, 4), "share": round(tot / total_ms, 4), "calls": n}
+        ab = algorithmic_bytes(name, P, M, Cs, D, C)
+        if ab is not None:
+            st["GBps"] = round(ab / (ms * 1e-3) / 1e9, 1)
+            st["hbm_frac"] = round(st["GBps"] / hbm, 3)
+        if name.startswith("alpha_blending"):
+            st["Gpairs_per_s"] = round(pairs / (ms * 1e-3) / 1e9, 2)
+        stages[name] = st
+    dom = next(iter(stages))
+    roof = {"kernel": dom}
+    if dom.startswith("alpha_blending"):
+        bwd = dom.endswith("backward")
+        lane_ops = (32 + 5 * C) if bwd else (13 + C)
+        mufu = 2 if bwd else 1
+        peak = min(sms * 128 * f_hz / lane_ops, sms * 16 * f_hz / mufu) / 1e9
+        ach = stages[dom]["Gpairs_per_s"]
+        roof.update({"bound": "fp32_issue", "achieved": ach, "peak": round(peak, 1), "unit": "Gpairs/s",
+                     "frac": round(ach / peak, 4), "traffic": None,
+                     "note": f"pair = sum(ncontrib) = {pairs} per render (SURVEY 8d); peak = min(SMs*128*f/"
+                             f"{lane_ops} lane-ops, SMs*16*f/{mufu} MUFU) at {sms} SMs, f = {f_hz/1e6:.0f} MHz "
+                             f"(clock observed during the run); the call also contains 2 helper launches"})
+    else:
+        ach = stages[dom].get("GBps", 0.0)
+        roof.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
+                     "traffic": None, "note": f"peak: {src}"})
+    # secondary: the HBM-bound sort (the north star asks for its achieved GB/s)
+    if "sort_gaussian" in stages:
+        s = stages["sort_gaussian"]
+        s["Gkeys_per_s"] = round(M / (s["ms"] * 1e-3) / 1e9, 3)
+        s["note"] = f"M = {M} keys, 6 onesweep passes over 45 significant bits, 172 B/key algorithmic; peak {hbm} GB/s {src}"
+    return {"roofline": roof, "stages": stages, "pairs_per_render": pairs, "keys_per_render": M}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle port (cpu_baseline / --impl oracle)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, sample=None):
+    import oracle
+    from msplat_b200.scenes import frustum_scene
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P, W, H = args.gaussians, args.width, args.height
+    Ps = sample or min(P, 1_000_000)
+    sc = frustum_scene(P, W, H, SIGMA, seed=0, sh_degree=SH_DEG)
+    params = [t[:Ps].clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
+    center = sc.cam_center
+    G = torch.randn(4, H, W, generator=torch.Generator().manual_seed(1))
+
+    class Api:
+        project_point = staticmethod(oracle.project_point)
+        compute_sh = staticmethod(oracle.compute_sh)
+        compute_cov3d = staticmethod(lambda s, q, v: oracle.compute_cov3d(s, q, v.reshape(-1)))
+        ewa_project = staticmethod(lambda x, c, i, e, uv, W, H, v: oracle.ewa_project(x, c, i, e, uv, W, H, v.reshape(-1)))
+        sort_gaussian = staticmethod(oracle.sort_gaussian)
+        alpha_blending = staticmethod(oracle.alpha_blending)
+
+    oracle.steps.build_blend_ref()
+    t0 = time.time()
+    render_once(Api, params, (sc.intr, sc.extr, center), W, H, G)
+    dt = time.time() - t0
+    scale = P / Ps
+    return {"value": 1.0 / (dt * scale), "unit": "renders/s", "cores": cores, "kind": "port",
+            "sample": f"one fwd+bwd render of the first {Ps} of the {P} Gaussians at {W}x{H} by the CPU oracle "
+                      f"(torch + C/OpenMP blend) in {dt:.1f} s on {cores} threads; value extrapolated x{scale:.0f} "
+                      f"linearly in P"}
+
+
+def run_oracle(args, as_reference=False):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args)
+    out = {"metric": METRIC, "value": cb["value"], "unit": "renders/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+           "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "impl": "reference" if as_reference else "oracle",
+           "config": {"workload": cb["sample"]}, "cpu_baseline": cb, "gpu_launches": 0,
+           "e2e": {"value": cb["value"], "unit": "renders/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def import_reference():
+    p = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(p, "msplat")):
+        return None
+    sys.path.insert(0, p)
+    try:
+        import msplat
+        return msplat
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "oracle"])
+    ap.add_argument("--views", type=int, default=4, help="renders per rank per step")
+    ap.add_argument("--gaussians", type=int, default=P_FULL)
+    ap.add_argument("--width", type=int, default=W_FULL)
+    ap.add_argument("--height", type=int, default=H_FULL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "oracle":
+        return run_oracle(args)
+    if args.impl == "reference":
+        ref = import_reference()
+        if ref is None or not torch.cuda.is_available():
+            return run_oracle(args, as_reference=True)
+        return run_gpu(args, ref, "reference")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: msplat_b200 has no CPU path")
+    import msplat_b200
+    run_gpu(args, msplat_b200, "ours")
+
+
+if __name__ == "__main__":
+    main()

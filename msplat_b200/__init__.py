@@ -10,7 +10,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, check, ptr, stream_ptr
+from ._lib import as_f32, ptr
 from .alpha_blending import _blend_backward, _blend_forward, alpha_blending
 from .compute_cov3d import compute_cov3d
 from .compute_sh import compute_sh
@@ -71,11 +71,8 @@ class _Rasterize(torch.autograd.Function):
         conic = torch.empty((P, 3), dtype=torch.float32, device=dev)
         radius = torch.empty((P,), dtype=torch.int32, device=dev)
         tiles = torch.empty((P,), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            check(_lib.lib().msb_preprocess_fwd(ptr(x), ptr(s), ptr(q), ptr(i), ptr(e), P, int(W), int(H), 0.0, 1.3,
-                                                ptr(uv), ptr(depth), ptr(conic), ptr(radius), ptr(tiles),
-                                                stream_ptr(dev)), "preprocess_forward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("preprocess_forward", 1 if P else 0, _lib.lib().msb_preprocess_fwd, dev, ptr(x), ptr(s), ptr(q),
+                  ptr(i), ptr(e), P, int(W), int(H), 0.0, 1.3, ptr(uv), ptr(depth), ptr(conic), ptr(radius), ptr(tiles))
         ids, tr = sort_gaussian(uv, depth, W, H, radius, tiles)
         image, final_T, ncontrib, packed = _blend_forward(uv, conic, o, f, ids, tr, bg, W, H)
         ctx.W, ctx.H, ctx.bg = W, H, bg
@@ -101,12 +98,9 @@ class _Rasterize(torch.autograd.Function):
         need_i, need_e = ctx.cam_grad
         dL_dintr = torch.zeros(4, dtype=torch.float32, device=dev) if need_i else None
         dL_dextr = torch.zeros(ctx.extr_shape, dtype=torch.float32, device=dev) if need_e else None
-        with torch.cuda.device(dev):
-            check(_lib.lib().msb_preprocess_bwd(ptr(x), ptr(s), ptr(q), ptr(i), ptr(e), ptr(depth), ptr(radius),
-                                                ptr(dL_duv), None, ptr(dL_dconic), P, ptr(dL_dxyz), ptr(dL_dscale),
-                                                ptr(dL_dquat), ptr(dL_dintr), ptr(dL_dextr), stream_ptr(dev)),
-                  "preprocess_backward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("preprocess_backward", 1 if P else 0, _lib.lib().msb_preprocess_bwd, dev, ptr(x), ptr(s), ptr(q),
+                  ptr(i), ptr(e), ptr(depth), ptr(radius), ptr(dL_duv), None, ptr(dL_dconic), P, ptr(dL_dxyz),
+                  ptr(dL_dscale), ptr(dL_dquat), ptr(dL_dintr), ptr(dL_dextr))
         dL_dndc = None
         if ctx.has_ndc:
             dL_dndc = dL_duv * torch.tensor([0.5 * W, 0.5 * H], dtype=dL_duv.dtype, device=dev)[None, :]

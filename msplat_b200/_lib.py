@@ -88,6 +88,28 @@ def check(rc: int, what: str):
         raise RuntimeError(f"msplat_b200.{what} failed (code {rc}): {msg}")
 
 
+# When set to a list, every C-ABI call is bracketed by CUDA events on the launching stream and
+# (name, start_event, end_event) is appended: bench.py uses it for per-kernel roofline numbers.
+TIMING = None
+
+
+def call(what: str, nlaunch: int, fn, device, *args):
+    """Invoke one C-ABI entry point on `device`'s current stream; raise on a non-zero status."""
+    global _launches
+    with torch.cuda.device(device):
+        st = stream_ptr(device)
+        if TIMING is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args, st)
+            e1.record()
+            TIMING.append((what, e0, e1))
+        else:
+            rc = fn(*args, st)
+    check(rc, what)
+    _launches += nlaunch
+
+
 def count_launches(n: int):
     global _launches
     _launches += n

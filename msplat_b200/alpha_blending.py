@@ -7,7 +7,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, as_i32, check, ptr, stream_ptr
+from ._lib import as_f32, as_i32, ptr
 
 
 def alpha_blending(
@@ -27,13 +27,11 @@ def _blend_forward(u, c, o, f, ids, tr, bg, W, H):
     final_T = torch.empty((H, W), dtype=torch.float32, device=dev)
     ncontrib = torch.empty((H, W), dtype=torch.int32, device=dev)
     packed = torch.empty((L.msb_blend_fwd_workspace_bytes(P, C),), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        check(L.msb_alpha_blending_fwd(ptr(u), ptr(c), ptr(o), ptr(f), ptr(ids), ptr(tr), float(bg), P, C, int(W),
-                                       int(H), ptr(image), ptr(final_T), ptr(ncontrib), ptr(packed), packed.numel(),
-                                       stream_ptr(dev)), "alpha_blending_forward")
     cpad = L.msb_blend_cpad(C)
     npass = 1 if C == 0 else (cpad // 32 + (1 if cpad % 32 else 0))
-    _lib.count_launches((1 if P else 0) + npass)
+    _lib.call("alpha_blending_forward", (1 if P else 0) + npass, L.msb_alpha_blending_fwd, dev, ptr(u), ptr(c), ptr(o),
+              ptr(f), ptr(ids), ptr(tr), float(bg), P, C, int(W), int(H), ptr(image), ptr(final_T), ptr(ncontrib),
+              ptr(packed), packed.numel())
     return image, final_T, ncontrib, packed
 
 
@@ -50,13 +48,11 @@ def _blend_backward(f, ids, tr, bg, W, H, final_T, ncontrib, g, packed):
             t.zero_()
         return dL_duv, dL_dconic, dL_dopacity, dL_dfeature
     ws = torch.empty((L.msb_blend_bwd_workspace_bytes(P, C),), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        check(L.msb_alpha_blending_bwd(ptr(f), ptr(ids), ptr(tr), float(bg), P, C, int(W), int(H), ptr(final_T),
-                                       ptr(ncontrib), ptr(g), ptr(packed), ptr(dL_duv), ptr(dL_dconic),
-                                       ptr(dL_dopacity), ptr(dL_dfeature), ptr(ws), ws.numel(), stream_ptr(dev)),
-              "alpha_blending_backward")
     cpad = L.msb_blend_cpad(C)
-    _lib.count_launches(1 + (cpad + 15) // 16 if cpad > 8 else 2)
+    nk = 1 + ((cpad + 15) // 16 if cpad > 8 else 1)
+    _lib.call("alpha_blending_backward", nk, L.msb_alpha_blending_bwd, dev, ptr(f), ptr(ids), ptr(tr), float(bg), P, C,
+              int(W), int(H), ptr(final_T), ptr(ncontrib), ptr(g), ptr(packed), ptr(dL_duv), ptr(dL_dconic),
+              ptr(dL_dopacity), ptr(dL_dfeature), ptr(ws), ws.numel())
     return dL_duv, dL_dconic, dL_dopacity, dL_dfeature
 
 

@@ -7,7 +7,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, as_mask, check, ptr, stream_ptr
+from ._lib import as_f32, as_mask, ptr
 
 
 def compute_cov3d(scales: Tensor, uquats: Tensor, visible: Tensor = None) -> Tensor:
@@ -26,10 +26,8 @@ class _ComputeCov3D(torch.autograd.Function):
         P = s.shape[0]
         vis = as_mask(visible, "visible", P)
         cov3d = torch.empty((P, 6), dtype=torch.float32, device=s.device)
-        with torch.cuda.device(s.device):
-            check(_lib.lib().msb_compute_cov3d_fwd(ptr(s), ptr(q), ptr(vis), P, ptr(cov3d), stream_ptr(s.device)),
-                  "compute_cov3d_forward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("compute_cov3d_forward", 1 if P else 0, _lib.lib().msb_compute_cov3d_fwd, s.device, ptr(s), ptr(q),
+                  ptr(vis), P, ptr(cov3d))
         ctx.save_for_backward(s, q, vis)
         return cov3d
 
@@ -40,8 +38,6 @@ class _ComputeCov3D(torch.autograd.Function):
         g = as_f32(dL_dcov3d, "dL_dcov3d")
         dL_ds = torch.empty((P, 3), dtype=torch.float32, device=s.device)
         dL_dq = torch.empty((P, 4), dtype=torch.float32, device=s.device)
-        with torch.cuda.device(s.device):
-            check(_lib.lib().msb_compute_cov3d_bwd(ptr(s), ptr(q), ptr(vis), ptr(g), P, ptr(dL_ds), ptr(dL_dq),
-                                                   stream_ptr(s.device)), "compute_cov3d_backward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("compute_cov3d_backward", 1 if P else 0, _lib.lib().msb_compute_cov3d_bwd, s.device, ptr(s), ptr(q),
+                  ptr(vis), ptr(g), P, ptr(dL_ds), ptr(dL_dq))
         return dL_ds, dL_dq, None

@@ -7,7 +7,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, as_mask, check, ptr, stream_ptr
+from ._lib import as_f32, as_mask, ptr
 
 
 def compute_sh(shs: Tensor, view_dirs: Tensor, visible: Tensor = None) -> Tensor:
@@ -29,10 +29,8 @@ class _ComputeSH(torch.autograd.Function):
             raise RuntimeError(f"shs last dim must be (deg+1)^2 with deg <= 10, got {D}")
         vis = as_mask(visible, "visible", P)
         value = torch.empty((P, Cs), dtype=torch.float32, device=s.device)
-        with torch.cuda.device(s.device):
-            check(_lib.lib().msb_compute_sh_fwd(ptr(s), ptr(d), ptr(vis), P, Cs, D, ptr(value), stream_ptr(s.device)),
-                  "compute_sh_forward")
-        _lib.count_launches(1 if P and Cs else 0)
+        _lib.call("compute_sh_forward", 1 if P and Cs else 0, _lib.lib().msb_compute_sh_fwd, s.device, ptr(s), ptr(d),
+                  ptr(vis), P, Cs, D, ptr(value))
         ctx.save_for_backward(s, d, vis)
         return value
 
@@ -46,8 +44,6 @@ class _ComputeSH(torch.autograd.Function):
         if Cs == 0:
             dL_ddirs.zero_()
         else:
-            with torch.cuda.device(s.device):
-                check(_lib.lib().msb_compute_sh_bwd(ptr(s), ptr(d), ptr(vis), ptr(g), P, Cs, D, ptr(dL_dshs),
-                                                    ptr(dL_ddirs), stream_ptr(s.device)), "compute_sh_backward")
-            _lib.count_launches(1 if P else 0)
+            _lib.call("compute_sh_backward", 1 if P else 0, _lib.lib().msb_compute_sh_bwd, s.device, ptr(s), ptr(d),
+                      ptr(vis), ptr(g), P, Cs, D, ptr(dL_dshs), ptr(dL_ddirs))
         return dL_dshs, dL_ddirs, None

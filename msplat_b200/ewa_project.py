@@ -9,7 +9,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, as_i32, as_mask, check, ptr, stream_ptr
+from ._lib import as_f32, as_mask, ptr
 
 
 def ewa_project(
@@ -34,11 +34,8 @@ class _EWAProject(torch.autograd.Function):
         conic = torch.empty((P, 3), dtype=torch.float32, device=dev)
         radius = torch.empty((P,), dtype=torch.int32, device=dev)
         tiles = torch.empty((P,), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            check(_lib.lib().msb_ewa_project_fwd(ptr(x), ptr(c), ptr(i), ptr(e), ptr(u), ptr(vis), P, int(W), int(H),
-                                                 ptr(conic), ptr(radius), ptr(tiles), stream_ptr(dev)),
-                  "ewa_project_forward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("ewa_project_forward", 1 if P else 0, _lib.lib().msb_ewa_project_fwd, dev, ptr(x), ptr(c), ptr(i),
+                  ptr(e), ptr(u), ptr(vis), P, int(W), int(H), ptr(conic), ptr(radius), ptr(tiles))
         ctx.cam_grad = (intr.requires_grad, extr.requires_grad)
         ctx.extr_shape = tuple(extr.shape)
         ctx.save_for_backward(x, c, i, e, radius)
@@ -56,9 +53,6 @@ class _EWAProject(torch.autograd.Function):
         need_i, need_e = ctx.cam_grad
         dL_dintr = torch.zeros(4, dtype=torch.float32, device=dev) if need_i else None
         dL_dextr = torch.zeros(ctx.extr_shape, dtype=torch.float32, device=dev) if need_e else None
-        with torch.cuda.device(dev):
-            check(_lib.lib().msb_ewa_project_bwd(ptr(x), ptr(c), ptr(i), ptr(e), ptr(radius), ptr(g), P, ptr(dL_dxyz),
-                                                 ptr(dL_dcov3d), ptr(dL_dintr), ptr(dL_dextr), stream_ptr(dev)),
-                  "ewa_project_backward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("ewa_project_backward", 1 if P else 0, _lib.lib().msb_ewa_project_bwd, dev, ptr(x), ptr(c), ptr(i),
+                  ptr(e), ptr(radius), ptr(g), P, ptr(dL_dxyz), ptr(dL_dcov3d), ptr(dL_dintr), ptr(dL_dextr))
         return dL_dxyz, dL_dcov3d, dL_dintr, dL_dextr, None, None, None, None

@@ -9,7 +9,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import as_f32, check, ptr, stream_ptr
+from ._lib import as_f32, ptr
 
 
 def project_point(
@@ -35,11 +35,9 @@ class _ProjectPoint(torch.autograd.Function):
         P = xyz_c.shape[0]
         uv = torch.empty((P, 2), dtype=torch.float32, device=xyz_c.device)
         depth = torch.empty((P, 1), dtype=torch.float32, device=xyz_c.device)
-        with torch.cuda.device(xyz_c.device):
-            check(_lib.lib().msb_project_point_fwd(ptr(xyz_c), ptr(intr_c), ptr(extr_c), P, int(W), int(H),
-                                                   float(nearest), float(extent), ptr(uv), ptr(depth),
-                                                   stream_ptr(xyz_c.device)), "project_point_forward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("project_point_forward", 1 if P else 0, _lib.lib().msb_project_point_fwd, xyz_c.device,
+                  ptr(xyz_c), ptr(intr_c), ptr(extr_c), P, int(W), int(H), float(nearest), float(extent), ptr(uv),
+                  ptr(depth))
         ctx.W, ctx.H = W, H
         ctx.cam_grad = (intr.requires_grad, extr.requires_grad)
         ctx.extr_shape = tuple(extr.shape)
@@ -56,9 +54,6 @@ class _ProjectPoint(torch.autograd.Function):
         need_i, need_e = ctx.cam_grad
         dL_dintr = torch.zeros(4, dtype=torch.float32, device=dev) if need_i else None
         dL_dextr = torch.zeros(ctx.extr_shape, dtype=torch.float32, device=dev) if need_e else None
-        with torch.cuda.device(dev):
-            check(_lib.lib().msb_project_point_bwd(ptr(xyz), ptr(intr), ptr(extr), ptr(depth), ptr(g_uv), ptr(g_d),
-                                                   P, ptr(dL_dxyz), ptr(dL_dintr), ptr(dL_dextr), stream_ptr(dev)),
-                  "project_point_backward")
-        _lib.count_launches(1 if P else 0)
+        _lib.call("project_point_backward", 1 if P else 0, _lib.lib().msb_project_point_bwd, dev, ptr(xyz),
+                  ptr(intr), ptr(extr), ptr(depth), ptr(g_uv), ptr(g_d), P, ptr(dL_dxyz), ptr(dL_dintr), ptr(dL_dextr))
         return dL_dxyz, dL_dintr, dL_dextr, None, None, None, None

@@ -1,0 +1,67 @@
+"""The C-ABI boundary: the library loads, exports exactly what include/msplat_b200.h declares,
+validates arguments, and the Python layer fails loudly instead of falling back."""
+import os
+import re
+
+import pytest
+import torch
+
+import msplat_b200
+from msplat_b200 import _lib
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "msplat_b200.h")).read()
+    declared = set(re.findall(r"\b(msb_\w+)\s*\(", hdr))
+    bound = set(_lib.exported_symbols())  # getattr on each: raises if the .so lacks one
+    assert declared == bound
+    assert _lib.lib().msb_version() >= 100
+
+
+def test_public_api_names_match_reference():
+    # /root/reference/msplat/__init__.py:11-19
+    assert set(msplat_b200.__all__) == {"project_point", "compute_cov3d", "ewa_project", "sort_gaussian",
+                                        "compute_sh", "alpha_blending", "rasterization"}
+    import inspect
+    sig = inspect.signature(msplat_b200.project_point)
+    assert list(sig.parameters) == ["xyz", "intr", "extr", "W", "H", "nearest", "extent"]
+    assert sig.parameters["nearest"].default == 0.0 and sig.parameters["extent"].default == 1.3
+    assert list(inspect.signature(msplat_b200.alpha_blending).parameters) == [
+        "uv", "conic", "opacity", "feature", "idx_sorted", "tile_range", "bg", "W", "H", "ndc"]
+    assert list(inspect.signature(msplat_b200.rasterization).parameters)[:11] == [
+        "xyz", "scale", "rotate", "opacity", "feature", "intr", "extr", "W", "H", "bg", "ndc"]
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected (reference: CHECK_CUDA, include/utils.h:9-10); nothing routes to the oracle."""
+    xyz = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        msplat_b200.project_point(xyz, torch.ones(4), torch.eye(4)[:3], 64, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        msplat_b200.compute_sh(torch.zeros(4, 3, 16), torch.zeros(4, 3))
+    import subprocess, sys
+    out = subprocess.run([sys.executable, "-c", "import sys, msplat_b200; print('oracle' in sys.modules)"],
+                         cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stdout + out.stderr
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    assert L.msb_blend_cpad(3) == 4 and L.msb_blend_cpad(8) == 8 and L.msb_blend_cpad(33) == 48
+    assert L.msb_sort_num_passes(1920, 1080) == 6      # T = 8160 -> 13 tile bits -> 45 bits
+    assert L.msb_sort_num_passes(3840, 2160) == 6      # T = 32400 -> 47 bits
+    assert L.msb_sort_num_passes(256, 256) == 5        # T = 256 -> 40 bits
+    assert L.msb_sort_workspace_bytes(1000, 64, 64) > 1000 * 20
+    # negative P / null pointers are rejected before any launch
+    rc = L.msb_project_point_fwd(None, None, None, 5, 64, 64, 0.0, 1.3, None, None, None)
+    assert rc == -1 and b"project_point_fwd" in L.msb_last_error()
+    rc = L.msb_compute_sh_fwd(None, None, None, 5, 3, 17, None, None)
+    assert rc == -1

@@ -1,0 +1,172 @@
+"""The product's per-Gaussian / per-pair math (msplat_b200/csrc/{geom,sh_eval,blend_math}.cuh),
+compiled for the host by tools/host_check.cu, checked against the oracle on a CPU-only box.
+(On the host the MUFU approximations are IEEE ops, so this is a tolerance-level check; the
+bit-level parity against the reference CUDA build is asserted by the -m gpu tests.)
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+import oracle
+from conftest import fp
+
+T = torch.from_numpy
+
+
+def _camera(W, H):
+    th = 0.3
+    intr = torch.tensor([700.0, 710.0, W / 2, H / 2])
+    extr = torch.tensor([[math.cos(th), 0, math.sin(th), 0.1], [0, 1, 0, -0.2], [-math.sin(th), 0, math.cos(th), 4.0]])
+    return intr, extr
+
+
+def _c(t):
+    return np.ascontiguousarray(t.detach().numpy())
+
+
+def test_project_point_fwd_bwd(host_check):
+    torch.manual_seed(0)
+    P, W, H = 4000, 800, 600
+    xyz = torch.randn(P, 3) * 1.5
+    intr, extr = _camera(W, H)
+    uv_o, d_o = oracle.project_point(xyz, intr, extr, W, H)
+    uv, dep = np.zeros((P, 2), np.float32), np.zeros(P, np.float32)
+    host_check.hc_project_fwd(P, fp(_c(xyz)), fp(_c(intr)), fp(_c(extr)), W, H, ctypes.c_float(0.0),
+                              ctypes.c_float(1.3), fp(uv), fp(dep))
+    assert ((dep == 0) == (d_o.numpy()[:, 0] == 0)).all() and (dep == 0).sum() > 100
+    np.testing.assert_allclose(uv, uv_o.numpy(), rtol=1e-5, atol=2e-4)
+    np.testing.assert_array_equal(dep, d_o.numpy()[:, 0])
+    # near-plane culling (nearest > 0) -- test/test_project_points.py uses 0.2
+    uv_n, d_n = oracle.project_point(xyz, intr, extr, W, H, nearest=3.5)
+    host_check.hc_project_fwd(P, fp(_c(xyz)), fp(_c(intr)), fp(_c(extr)), W, H, ctypes.c_float(3.5),
+                              ctypes.c_float(1.3), fp(uv), fp(dep))
+    assert ((dep == 0) == (d_n.numpy()[:, 0] == 0)).all()
+    # backward incl. camera gradients, against float64 autograd of the oracle
+    x64 = xyz.double().requires_grad_()
+    i64, e64 = intr.double().requires_grad_(), extr.double().requires_grad_()
+    uv_r, d_r = oracle.project_point(x64, i64, e64, W, H)
+    guv, gd = torch.randn(P, 2), torch.randn(P)
+    ((uv_r * guv.double()).sum() + (d_r[:, 0] * gd.double()).sum()).backward()
+    dx, cam = np.zeros((P, 3), np.float32), np.zeros(16, np.float32)
+    host_check.hc_project_fwd(P, fp(_c(xyz)), fp(_c(intr)), fp(_c(extr)), W, H, ctypes.c_float(0.0),
+                              ctypes.c_float(1.3), fp(uv), fp(dep))
+    host_check.hc_project_bwd(P, fp(_c(xyz)), fp(_c(intr)), fp(_c(extr)), fp(dep), fp(_c(guv)), fp(_c(gd)), fp(dx),
+                              fp(cam))
+    np.testing.assert_allclose(dx, x64.grad.numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(cam[:4], i64.grad.numpy(), rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(cam[4:], e64.grad.numpy().reshape(-1), rtol=1e-3, atol=0.5)
+
+
+def test_cov3d_fwd_bwd(host_check):
+    torch.manual_seed(1)
+    P = 3000
+    s = torch.rand(P, 3) + 0.05
+    q = torch.randn(P, 4)  # deliberately NOT normalised
+    cov = np.zeros((P, 6), np.float32)
+    host_check.hc_cov3d_fwd(P, fp(_c(s)), fp(_c(q)), fp(cov))
+    np.testing.assert_allclose(cov, oracle.compute_cov3d(s, q).numpy(), rtol=1e-5, atol=1e-5)
+    s64, q64 = s.double().requires_grad_(), q.double().requires_grad_()
+    g = torch.randn(P, 6)
+    (oracle.compute_cov3d(s64, q64) * g.double()).sum().backward()
+    ds, dq = np.zeros((P, 3), np.float32), np.zeros((P, 4), np.float32)
+    host_check.hc_cov3d_bwd(P, fp(_c(s)), fp(_c(q)), fp(_c(g)), fp(ds), fp(dq))
+    np.testing.assert_allclose(ds, s64.grad.numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dq, q64.grad.numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_ewa_fwd_bwd(host_check):
+    torch.manual_seed(2)
+    P, W, H = 5000, 800, 600
+    xyz = torch.randn(P, 3) * 1.5
+    intr, extr = _camera(W, H)
+    uv, depth = oracle.project_point(xyz, intr, extr, W, H)
+    vis = (depth != 0).reshape(-1)
+    s = (torch.rand(P, 3) + 0.05) * 0.2
+    q = torch.randn(P, 4)
+    q = q / q.norm(dim=-1, keepdim=True)
+    cov = oracle.compute_cov3d(s, q, vis)
+    conic_o, rad_o, til_o = oracle.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+    conic, rad, til = np.zeros((P, 3), np.float32), np.zeros(P, np.int32), np.zeros(P, np.int32)
+    host_check.hc_ewa_fwd(P, fp(_c(xyz)), fp(_c(cov)), fp(_c(intr)), fp(_c(extr)), fp(_c(uv)),
+                          fp(_c(vis).astype(np.uint8)), W, H, fp(conic), fp(rad), fp(til))
+    # integer outputs may differ only where 3*sqrt(lambda) sits within an ulp of an integer
+    assert (rad != rad_o.numpy()).mean() < 2e-3 and (til != til_o.numpy()).mean() < 2e-3
+    same = rad == rad_o.numpy()
+    np.testing.assert_allclose(conic[same], conic_o.numpy()[same], rtol=2e-4, atol=1e-6)
+    assert (til > 0).sum() > 1000
+    x64, c64 = xyz.double().requires_grad_(), cov.double().requires_grad_()
+    i64, e64 = intr.double().requires_grad_(), extr.double().requires_grad_()
+    c_r, _, _ = oracle.ewa_project(x64, c64, i64, e64, uv.double(), W, H, vis)
+    gc = torch.randn(P, 3)
+    (c_r * gc.double()).sum().backward()
+    dx, dcov, cam = np.zeros((P, 3), np.float32), np.zeros((P, 6), np.float32), np.zeros(16, np.float32)
+    host_check.hc_ewa_bwd(P, fp(_c(xyz)), fp(_c(cov)), fp(_c(intr)), fp(_c(extr)), fp(_c(rad_o)), fp(_c(gc)), fp(dx),
+                          fp(dcov), fp(cam))
+    sx, sc = np.abs(x64.grad.numpy()).max(), np.abs(c64.grad.numpy()).max()
+    assert np.abs(dx - x64.grad.numpy()).max() < 1e-4 * sx
+    assert np.abs(dcov - c64.grad.numpy()).max() < 1e-4 * sc
+    np.testing.assert_allclose(cam[:2], i64.grad.numpy()[:2], rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(cam[4:], e64.grad.numpy().reshape(-1), rtol=2e-3, atol=1e-3)
+
+
+def test_sh_basis_and_gradient(host_check, golden):
+    g = golden("sh_basis.npz")
+    dirs = g["dirs"][:64].astype(np.float32)  # unit directions
+    for deg in range(11):
+        D = (deg + 1) ** 2
+        out = np.zeros((64, D), np.float32)
+        assert host_check.hc_sh_basis(deg, 64, fp(dirs), fp(out)) == 0
+        ref = oracle.sh_basis(T(dirs.astype(np.float64)), D).numpy()
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=5e-5 if deg <= 6 else 5e-4)
+        d64 = T(dirs.astype(np.float64)).requires_grad_()
+        w = torch.randn(64, D, dtype=torch.float64)
+        ((oracle.sh_basis(d64, D) * w).sum() + 0.0 * d64.sum()).backward()  # deg 0 has no dir dependence
+        gout = np.zeros((64, 3), np.float32)
+        assert host_check.hc_sh_grad(deg, 64, fp(dirs), fp(_c(w.float())), fp(gout)) == 0
+        scale = max(float(d64.grad.abs().max()), 1.0)
+        assert np.abs(gout - d64.grad.numpy()).max() < 2e-4 * scale, deg
+    # off the unit sphere the same polynomials must hold (dL_ddir is their derivative): relative check
+    off = g["dirs"][64:].astype(np.float32)
+    out = np.zeros((64, 121), np.float32)
+    host_check.hc_sh_basis(10, 64, fp(off), fp(out))
+    ref = g["basis_cuda_text"][64:]
+    assert np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1.0)) < 2e-3
+
+
+def test_blend_pair_math_and_cull_extent(host_check):
+    """One pixel over a random list: product pair math == oracle C loop; and the culling box never
+    excludes a pair that passes the alpha test."""
+    rng = np.random.default_rng(5)
+    n, C = 300, 4
+    uv = (rng.random((n, 2)) * 16).astype(np.float32)
+    A = rng.normal(size=(n, 2, 2)) * 0.4
+    cv = A @ A.transpose(0, 2, 1) + 0.05 * np.eye(2)
+    cinv = np.linalg.inv(cv)
+    conic = np.stack([cinv[:, 0, 0], cinv[:, 0, 1], cinv[:, 1, 1]], -1).astype(np.float32)
+    op = rng.random(n).astype(np.float32)
+    op[:20] *= 0.0035  # below 1/255: can never pass the alpha test
+    feat = rng.random((n, C)).astype(np.float32)
+    F, last = np.zeros(C, np.float32), ctypes.c_int(0)
+    host_check.hc_blend_pixel.restype = ctypes.c_float
+    Tf = host_check.hc_blend_pixel(n, fp(uv), fp(conic), fp(op), fp(feat), C, ctypes.c_float(7.0), ctypes.c_float(5.0),
+                                   fp(F), ctypes.byref(last))
+    # oracle: a 16x16 image whose single tile lists all n Gaussians in order
+    ids = torch.arange(n, dtype=torch.int32)
+    tr = torch.tensor([[0, n]], dtype=torch.int32)
+    img, fT, nc, _ = oracle.alpha_blending_forward(T(uv), T(conic), T(op), T(feat), ids, tr, 0.0, 16, 16)
+    np.testing.assert_allclose(F, img[:, 5, 7].numpy(), rtol=1e-5, atol=1e-6)
+    assert abs(Tf - float(fT[5, 7])) < 1e-6 and last.value == int(nc[5, 7])
+    # culling extents are conservative
+    hxy = np.zeros((n, 2), np.float32)
+    host_check.hc_cull_extent(n, fp(conic), fp(op), fp(hxy))
+    ys, xs = np.mgrid[0:16, 0:16]
+    for j in range(n):
+        dx, dy = uv[j, 0] - xs, uv[j, 1] - ys
+        power = -0.5 * (conic[j, 0] * dx * dx + conic[j, 2] * dy * dy) - conic[j, 1] * dx * dy
+        alpha = np.minimum(0.99, op[j] * np.exp(power))
+        passes = (power <= 0) & (alpha >= 1.0 / 255.0)
+        if passes.any():
+            assert (np.abs(dx[passes]) <= hxy[j, 0]).all() and (np.abs(dy[passes]) <= hxy[j, 1]).all(), j
+    assert (hxy[:20] < 0).all()  # opacity < 1/255 can never contribute
