@@ -294,7 +294,10 @@ def test_sort_known_answer(ms):
     assert ids.tolist() == ka["idx_sorted"] and tr.tolist() == ka["tile_range"]
 
 
-def _sort_inputs(P, W, H, seed, scale_mul=1.0, tie_depth=False):
+def _sort_inputs(P, W, H, seed, scale_mul=1.0, tie_depth=False, keep_negative_depth=False):
+    """keep_negative_depth=False removes Gaussians behind the camera (radius = tiles = 0): with the
+    API default nearest=0 they are not culled and the reference's key kernel sign-extends their
+    depth bits over the tile id (UB), so they cannot be part of a reference comparison."""
     xyz, scale, quat, _ = cloud(P, seed=seed)
     intr, extr = camera(W, H)
     uv, depth = oracle.project_point(xyz, intr, extr, W, H)
@@ -303,6 +306,10 @@ def _sort_inputs(P, W, H, seed, scale_mul=1.0, tie_depth=False):
     vis = (depth != 0).reshape(-1)
     cov = oracle.compute_cov3d(scale * scale_mul, quat, vis)
     conic, radius, tiles = oracle.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+    if not keep_negative_depth:
+        neg = depth.reshape(-1) < 0
+        radius = torch.where(neg, torch.zeros_like(radius), radius)
+        tiles = torch.where(neg, torch.zeros_like(tiles), tiles)
     return uv, depth, radius, tiles
 
 
@@ -310,7 +317,8 @@ def _sort_inputs(P, W, H, seed, scale_mul=1.0, tie_depth=False):
                                            (3000, 512, 512, 30.0, False), (200, 64, 48, 1.0, True),
                                            (4097, 256, 256, 0.3, False)])
 def test_sort_vs_oracle(ms, P, W, H, mul, tie):
-    uv, depth, radius, tiles = _sort_inputs(P, W, H, 11, mul, tie)
+    # includes Gaussians behind the camera: depth bits are masked to 32 bits (defined behaviour)
+    uv, depth, radius, tiles = _sort_inputs(P, W, H, 11, mul, tie, keep_negative_depth=True)
     ids_o, tr_o = oracle.sort_gaussian(uv, depth, W, H, radius, tiles)
     ids, tr = ms.sort_gaussian(uv.to(DEV), depth.to(DEV), W, H, radius.to(DEV), tiles.to(DEV))
     assert ids.shape == ids_o.shape
