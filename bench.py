@@ -7,11 +7,15 @@ RGB+depth (BASELINE.json configs[2], SURVEY 8d "Config #3").
         --master-port P bench.py --gpus N --steps K --warmup W
 
 One STEP = `views` (default 4) fwd+bwd renders of the same resident 3M-Gaussian cloud from
-different cameras through the public steps API
-    project_point -> compute_sh(+0.5, clamp) -> cat(rgb, depth) -> compute_cov3d -> ewa_project
-    -> sort_gaussian -> alpha_blending -> (image * G).sum().backward()
-with gradients to xyz, scale, rotation, opacity and SH coefficients accumulated in one flat
-buffer.  With N > 1 every rank renders its own `views` cameras (weak scaling) and the flat
+different cameras, loss = sum(image * G), gradients to xyz, scale, rotation, opacity and SH
+coefficients summed over the views.  Two ways to write that step against the public API:
+  --api steps  the chain the reference offers (and the only one it has):
+                 project_point -> compute_sh(+0.5, clamp) -> cat(rgb, depth) -> compute_cov3d ->
+                 ewa_project -> sort_gaussian -> alpha_blending -> backward, once per view
+  --api fused  msplat_b200.rasterization_sh_views: the same maths as ONE autograd Function over
+               the view batch (fused per-Gaussian kernels, gradients accumulated in-kernel);
+               default for --impl ours, which also reports the steps-API number as `steps_api`
+With N > 1 every rank renders its own `views` cameras (weak scaling) and the per-Gaussian
 gradients are sum-all-reduced once per step (NCCL).  value = N * views / step_time.
 
 --impl ours       msplat_b200 (default)
@@ -136,8 +140,15 @@ def measured_peaks():
 
 
 # algorithmic HBM bytes per unit of each C-ABI call at SH3 RGB + depth (DESIGN.md "Kernels")
-def algorithmic_bytes(name, P, M, Cs, D, C):
+def algorithmic_bytes(name, P, M, Cs, D, C, nvis=None, views=1):
+    nvis = P if nvis is None else nvis
+    sh = 4 * Cs * D
+    # backward: the first view of a step writes every output, the others accumulate (read + write)
+    acc = (views - 1) / max(views, 1)
     T = {
+        "render_preprocess_forward": P * (44 + 32 + 16 + 8 + 12) + nvis * sh,
+        "render_preprocess_backward": P * (40 + 32 + 16 + 4) + nvis * sh + P * 44 * (1 + acc)
+                                      + (1 - acc) * P * sh + acc * nvis * 2 * sh,
         "project_point_forward": P * (12 + 12),
         "project_point_backward": P * (12 + 4 + 12 + 12),
         "compute_cov3d_forward": P * (12 + 16 + 1 + 24),
@@ -169,93 +180,118 @@ def run_gpu(args, api, impl):
     from msplat_b200.parallel import FlatGrads
     from msplat_b200.scenes import frustum_scene
 
+    ours = impl == "ours"
     P, W, H = args.gaussians, args.width, args.height
     scene = frustum_scene(P, W, H, SIGMA, seed=0, sh_degree=SH_DEG).to(dev)
     params = [t.clone().requires_grad_() for t in (scene.xyz, scene.scale, scene.quat, scene.opacity, scene.shs)]
-    grads = FlatGrads(params)
     V = args.views
     cams_host = make_cameras(scene, V * world, "cpu")[rank * V:(rank + 1) * V]
-    cams = [tuple(t.to(dev) for t in c) for c in cams_host]
     C = 4
     G_host = torch.randn(C, H, W, generator=torch.Generator().manual_seed(1)).pin_memory()
     G = G_host.to(dev)
+    # host-side (pinned) step inputs: cameras as [V,4] / [V,3,4] / [V,3] + the cotangent
+    intr_h = torch.stack([c[0] for c in cams_host]).pin_memory()
+    extr_h = torch.stack([c[1] for c in cams_host]).pin_memory()
+    cent_h = torch.stack([c[2] for c in cams_host]).pin_memory()
+    h2d = (intr_h.numel() + extr_h.numel() + cent_h.numel() + G_host.numel()) * 4
+    flat = FlatGrads(params)
 
-    def step(cams_, G_):
-        grads.zero_()
+    def step_steps(intrs, extrs, cents, G_):
+        """the reference-style chain, one backward per view, grads accumulated by autograd"""
+        flat.attach()
+        flat.zero_()
         total = None
-        for cam in cams_:
-            l = render_once(api, params, cam, W, H, G_)
+        for k in range(V):
+            l = render_once(api, params, (intrs[k], extrs[k], cents[k]), W, H, G_)
             total = l if total is None else total + l
-        grads.all_reduce()
+        flat.all_reduce()
         return total
 
-    for _ in range(args.warmup):
-        step(cams, G)
-    ours = impl == "ours"
+    def step_fused(intrs, extrs, cents, G_):
+        """one autograd Function over the view batch; gradients come back already summed"""
+        for p_ in params:
+            p_.grad = None
+        images = api.rasterization_sh_views(*params, intrs, extrs, W, H, 0.0, with_depth=True)
+        loss = (images * G_).sum()
+        loss.backward()
+        if world > 1:
+            works = [dist.all_reduce(p_.grad, op=dist.ReduceOp.SUM, async_op=True) for p_ in params]
+            for w_ in works:
+                w_.wait()
+        return loss.detach()
+
+    def measure(step):
+        """-> (ms per step resident, renders/s resident, renders/s e2e, launches, timing)"""
+        dev_in = (intr_h.to(dev), extr_h.to(dev), cent_h.to(dev), G)
+        for _ in range(args.warmup):
+            step(*dev_in)
+        barrier_sync(world)
+        if ours:
+            _lib.reset_launches()
+            _lib.TIMING = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(args.steps):
+            step(*dev_in)
+        e1.record()
+        barrier_sync(world)
+        t1 = time.time()
+        launches = _lib.launches() if ours else 0
+        timing = _lib.TIMING if ours else None
+        if ours:
+            _lib.TIMING = None
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        # e2e: per step H2D of the step's inputs (cameras + cotangent) from pinned memory, D2H of the loss
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        barrier_sync(world)
+        e0.record()
+        for _ in range(args.steps):
+            ins = (intr_h.to(dev, non_blocking=True), extr_h.to(dev, non_blocking=True),
+                   cent_h.to(dev, non_blocking=True), G_host.to(dev, non_blocking=True))
+            tot = step(*ins)
+            loss_host.copy_(tot.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+        e1.record()
+        barrier_sync(world)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = world * V * args.steps
+        return ms / args.steps, n / (ms / 1e3), n / (float(t[0]) / 1e3), launches, timing, (t0, t1)
+
     if ours:
         from msplat_b200 import _lib
-    # ---------------- timed region: inputs resident in HBM ----------------
+    fused = ours and args.api == "fused"
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
-    barrier_sync(world)
-    if ours:
-        _lib.reset_launches()
-        _lib.TIMING = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step(cams, G)
-    e1.record()
-    barrier_sync(world)
-    t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launches() if ours else None
-    timing = _lib.TIMING if ours else None
-    if ours:
-        _lib.TIMING = None
+    ms_per_step, value, e2e_value, launches, timing, (t_wall0, t_wall1) = measure(step_fused if fused else step_steps)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
-    ms_per_step = ms / args.steps
-    value = world * V * args.steps / (ms / 1e3)
 
-    # ---------------- e2e: per step H2D of the step's inputs (cameras + cotangent), D2H of the loss ----------
-    cam_pinned = [tuple(t.pin_memory() for t in c) for c in cams_host]
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-    h2d = sum(sum(t.numel() * 4 for t in c) for c in cam_pinned) + G_host.numel() * 4
-    barrier_sync(world)
-    e0.record()
-    for _ in range(args.steps):
-        cams_e = [tuple(t.to(dev, non_blocking=True) for t in c) for c in cam_pinned]
-        G_e = G_host.to(dev, non_blocking=True)
-        tot = step(cams_e, G_e)
-        loss_host.copy_(tot.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
-    e1.record()
-    barrier_sync(world)
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * V * args.steps / (float(t[0]) / 1e3)
-
+    api_note = ("msplat_b200.rasterization_sh_views (fused view-batch Function)" if fused else
+                "steps API: project_point/compute_sh/compute_cov3d/ewa_project/sort_gaussian/alpha_blending per view")
     out = {
         "metric": METRIC, "value": value, "unit": "renders/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"S-frustum(P={P}, {W}x{H}, sigma_med={SIGMA}, seed=0), SH degree {SH_DEG}, "
                                f"RGB+depth (C=4), fwd+bwd, {V} views per rank per step, grads to xyz/scale/rot/"
-                               f"opacity/shs" + (", one NCCL sum all-reduce of the flat grads per step" if world > 1 else ""),
+                               f"opacity/shs" + (", one NCCL sum all-reduce of the grads per step" if world > 1 else ""),
                    "gaussians": P, "width": W, "height": H, "sh_degree": SH_DEG, "channels": C,
-                   "views_per_rank_per_step": V, "parallelism": f"view-dp{world}",
+                   "views_per_rank_per_step": V, "parallelism": f"view-dp{world}", "api": api_note,
                    "cache": "inputs (~0.7 GB of parameters per render) exceed the 126 MB L2; no explicit flush"},
         "impl": impl, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "renders/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
     }
     if ours:
         out["gpu_launches"] = launches
-        out.update(stage_report(timing, args, api, params, cams[0], G, clocks))
+        out.update(stage_report(timing, args, api, params, cams_host[0], G, clocks, V))
+        if fused and not args.no_steps_api:
+            s_ms, s_val, s_e2e, _, _, _ = measure(step_steps)
+            out["steps_api"] = {"value": s_val, "e2e": s_e2e, "ms_per_step": s_ms, "unit": "renders/s",
+                                "note": "same workload written against the reference-style steps API of msplat_b200"}
     else:
         out["gpu_launches"] = 0
         out["cpu_baseline"] = {"value": value, "unit": "renders/s", "cores": 0, "kind": "reference-cuda",
@@ -269,7 +305,7 @@ def run_gpu(args, api, impl):
         dist.destroy_process_group()
 
 
-def stage_report(timing, args, api, params, cam, G, clocks):
+def stage_report(timing, args, api, params, cam, G, clocks, views):
     """Per-C-ABI-call durations (CUDA events recorded on the launching stream inside the timed
     region) -> roofline of the dominant call + a per-stage table."""
     from msplat_b200 import _lib
@@ -280,10 +316,10 @@ def stage_report(timing, args, api, params, cam, G, clocks):
         d = agg.setdefault(name, [0.0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += 1
-    # pairs = sum(ncontrib) and M for one representative view
+    # pairs = sum(ncontrib), M and the number of Gaussians touching a tile, for one representative view
     with torch.no_grad():
         xyz, scale, quat, opacity, shs = [p.detach() for p in params]
-        intr, extr, center = cam
+        intr, extr = cam[0].to(xyz.device), cam[1].to(xyz.device)
         uv, depth = api.project_point(xyz, intr, extr, W, H)
         vis = depth != 0
         cov = api.compute_cov3d(scale, quat, vis)
@@ -294,24 +330,27 @@ def stage_report(timing, args, api, params, cam, G, clocks):
         _, _, ncontrib, _ = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
         pairs = int(ncontrib.sum())
         M = int(ids.numel())
+        nvis = int((tiles > 0).sum())
     hbm, sm_max, src = measured_peaks()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     f_hz = (clocks["sm_mhz"] if clocks else sm_max) * 1e6
     total_ms = sum(v[0] for v in agg.values())
+    is_blend = lambda n: n.startswith("alpha_blending") or n.startswith("blend_")
     stages = {}
     for name, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         ms = tot / n
         st = {"ms": round(ms, 4), "share": round(tot / total_ms, 4), "calls": n}
-        ab = algorithmic_bytes(name, P, M, Cs, D, C)
+        ab = algorithmic_bytes(name, P, M, Cs, D, C, nvis, views)
         if ab is not None:
             st["GBps"] = round(ab / (ms * 1e-3) / 1e9, 1)
             st["hbm_frac"] = round(st["GBps"] / hbm, 3)
-        if name.startswith("alpha_blending"):
+            st["algorithmic_MB"] = round(ab / 1e6, 1)
+        if is_blend(name):
             st["Gpairs_per_s"] = round(pairs / (ms * 1e-3) / 1e9, 2)
         stages[name] = st
     dom = next(iter(stages))
     roof = {"kernel": dom}
-    if dom.startswith("alpha_blending"):
+    if is_blend(dom):
         bwd = dom.endswith("backward")
         lane_ops = (32 + 5 * C) if bwd else (13 + C)
         mufu = 2 if bwd else 1
@@ -321,7 +360,8 @@ def stage_report(timing, args, api, params, cam, G, clocks):
                      "frac": round(ach / peak, 4), "traffic": None,
                      "note": f"pair = sum(ncontrib) = {pairs} per render (SURVEY 8d); peak = min(SMs*128*f/"
                              f"{lane_ops} lane-ops, SMs*16*f/{mufu} MUFU) at {sms} SMs, f = {f_hz/1e6:.0f} MHz "
-                             f"(clock observed during the run); the call also contains 2 helper launches"})
+                             f"(clock observed during the run); not an HBM/tensor kernel: DRAM traffic is <10% of "
+                             f"peak (profiles/), so `traffic` is not the limiter"})
     else:
         ach = stages[dom].get("GBps", 0.0)
         roof.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
@@ -331,7 +371,8 @@ def stage_report(timing, args, api, params, cam, G, clocks):
         s = stages["sort_gaussian"]
         s["Gkeys_per_s"] = round(M / (s["ms"] * 1e-3) / 1e9, 3)
         s["note"] = f"M = {M} keys, 6 onesweep passes over 45 significant bits, 172 B/key algorithmic; peak {hbm} GB/s {src}"
-    return {"roofline": roof, "stages": stages, "pairs_per_render": pairs, "keys_per_render": M}
+    return {"roofline": roof, "stages": stages, "pairs_per_render": pairs, "keys_per_render": M,
+            "gaussians_touching_a_tile": nvis}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -404,6 +445,9 @@ def main():
     ap.add_argument("--width", type=int, default=W_FULL)
     ap.add_argument("--height", type=int, default=H_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--api", default="fused", choices=["fused", "steps"],
+                    help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
+    ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "oracle":

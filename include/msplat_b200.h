@@ -116,6 +116,40 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
                            const float* dL_dimage, const void* packed, float* dL_duv, float* dL_dconic,
                            float* dL_dopacity, float* dL_dfeature, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- packed blend (inputs/gradients stay in the blend kernels' packed layout) --------------
+ * Same kernels as msb_alpha_blending_fwd/bwd (src/alpha_blending.cu:248-573) without the
+ * pack / unpack passes: rec [P,8] = {u, v, conic.x, conic.y | conic.z, opacity, hx, hy},
+ * featp [P,Cpad], Cpad = msb_blend_cpad(C); grec [P,8] = {dL_duv.xy, dL_dconic.xyz,
+ * dL_dopacity, 0, 0} and gfeat [P,Cpad] are zeroed and then accumulated by the backward call. */
+int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
+                         float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
+                         void* stream);
+int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
+                         float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
+                         const float* dL_dimage, float* grec, float* gfeat, void* stream);
+
+/* ---- fused SH render preprocess ------------------------------------------------------------
+ * One forward / one backward kernel for the whole per-Gaussian part of an SH-coloured render:
+ * replaces the sequence projectPointsForward (src/project_point.cu:147-179), computeCov3DForward
+ * (src/compute_cov3d.cu:149-170), EWAProjectForward (src/ewa_project.cu:254-297),
+ * computeSHForward (src/compute_sh.cu:1696-1721) plus the torch glue of a 3DGS trainer
+ * (view_dir = normalize(xyz - camera centre); colour = clamp_min(sh + sh_bias, 0);
+ * feature = cat(colour, depth)) -- and the matching *Backward functions.  The camera centre is
+ * -R^T t of extr.  shs [P,Cs,D], D = (deg+1)^2, deg <= 10.  C = Cs + (with_depth ? 1 : 0).
+ * uv/depth/radius/tiles are bit-identical to msb_project_point_fwd / msb_ewa_project_fwd.
+ * backward: accumulate != 0 adds into the outputs (view batches), else every element is written;
+ * dL_dintr [4] / dL_dextr [12] may be NULL, otherwise they are accumulated into. */
+int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* opacity,
+                              const float* shs, const float* intr, const float* extr, int P, int Cs, int D,
+                              int with_depth, int W, int H, float nearest, float extent, float sh_bias, int clamp,
+                              float* rec, float* featp, float* uv, float* depth, int32_t* radius, int32_t* tiles,
+                              void* stream);
+int msb_render_preprocess_bwd(const float* xyz, const float* scale, const float* quat, const float* shs,
+                              const float* intr, const float* extr, const int32_t* tiles, const float* grec,
+                              const float* gfeat, int P, int Cs, int D, int with_depth, float sh_bias, int clamp,
+                              int accumulate, float* dL_dxyz, float* dL_dscale, float* dL_dquat, float* dL_dopacity,
+                              float* dL_dshs, float* dL_dintr, float* dL_dextr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

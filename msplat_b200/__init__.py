@@ -16,6 +16,7 @@ from .compute_cov3d import compute_cov3d
 from .compute_sh import compute_sh
 from .ewa_project import ewa_project
 from .project_point import project_point
+from .render import rasterization_sh, rasterization_sh_views
 from .sort_gaussian import sort_gaussian
 
 __all__ = [
@@ -26,6 +27,9 @@ __all__ = [
     "compute_sh",
     "alpha_blending",
     "rasterization",
+    # extensions beyond the reference API (fused SH render path, csrc/render.cu)
+    "rasterization_sh",
+    "rasterization_sh_views",
 ]
 
 __version__ = "0.1.0"

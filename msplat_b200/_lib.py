@@ -52,6 +52,10 @@ def _declare(lib):
         "msb_blend_bwd_workspace_bytes": (SZ, [I, I]),
         "msb_alpha_blending_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P, P, P, P, SZ, V]),
         "msb_alpha_blending_bwd": (I, [P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, SZ, V]),
+        "msb_blend_packed_fwd": (I, [P, P, P, P, F, I, I, I, P, P, P, V]),
+        "msb_blend_packed_bwd": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, P, V]),
+        "msb_render_preprocess_fwd": (I, [P] * 7 + [I, I, I, I, I, I, F, F, F, I] + [P] * 6 + [V]),
+        "msb_render_preprocess_bwd": (I, [P] * 9 + [I, I, I, I, F, I, I] + [P] * 7 + [V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
@@ -172,14 +176,14 @@ def as_mask(t: torch.Tensor, name: str, n: int) -> torch.Tensor:
 _pinned = threading.local()
 
 
-def pinned_i64(device) -> torch.Tensor:
-    """A per-thread, per-device pinned int64[1] used for the sort stage's M read-back."""
+def pinned_i64(device, n: int = 1) -> torch.Tensor:
+    """A per-thread, per-device pinned int64[n] used for the sort stage's M read-back(s)."""
     cache = getattr(_pinned, "cache", None)
     if cache is None:
         cache = _pinned.cache = {}
     key = torch.device(device).index
-    if key not in cache:
-        cache[key] = torch.zeros(1, dtype=torch.int64).pin_memory()
+    if key not in cache or cache[key].numel() < n:
+        cache[key] = torch.zeros(max(n, 8), dtype=torch.int64).pin_memory()
     return cache[key]
 
 

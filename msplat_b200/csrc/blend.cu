@@ -437,6 +437,73 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float
     return check_launch("alpha_blending_bwd");
 }
 
+
+// channel-chunk dispatcher of the forward pass (reference D1: alpha_blending.cu:248-394)
+static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
+                          const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H, float* image,
+                          float* final_T, int32_t* ncontrib) {
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+    const int2* tr = reinterpret_cast<const int2*>(tile_range);
+    int c0 = 0, first = 1;
+    do {  // at least one pass so that final_T / ncontrib exist even for C == 0
+        const int rem = Cpad - c0;
+        const int ch = C == 0 ? 4 : pick_fwd_ch(rem);
+        const int c_valid = max(0, min(ch, C - c0));
+        float* img = image ? image + (size_t)c0 * H * W : nullptr;
+        int rc;
+        if (C == 0) {  // geometry-only pass: stage rec twice (no feature rows exist)
+            rc = launch_fwd<4>(grid, st, rec, reinterpret_cast<const float*>(rec), 8, 0, idx_sorted, tr, bg, 0, W, H, 1,
+                               final_T, ncontrib, img);
+        } else if (ch == 32) {
+            rc = launch_fwd<32>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                                ncontrib, img);
+        } else if (ch == 16) {
+            rc = launch_fwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                                ncontrib, img);
+        } else if (ch == 8) {
+            rc = launch_fwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                               ncontrib, img);
+        } else {
+            rc = launch_fwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
+                               ncontrib, img);
+        }
+        if (rc) return rc;
+        c0 += ch;
+        first = 0;
+    } while (c0 < C);
+    return MSB_OK;
+}
+
+// channel-chunk dispatcher of the backward pass; grec/gfeat must be zero on entry
+static int run_bwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
+                          const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H,
+                          const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
+                          float* gfeat) {
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+    const int2* tr = reinterpret_cast<const int2*>(tile_range);
+    for (int c0 = 0; c0 < C;) {
+        const int rem = Cpad - c0;
+        const int ch = pick_bwd_ch(rem);
+        const int c_valid = min(ch, C - c0);
+        const float* dimg = dL_dimage + (size_t)c0 * H * W;
+        int rc;
+        // geometric gradients are linear in the channels: every chunk adds its share (D1 in the
+        // reference does the same, alpha_blending.cu:436-567)
+        if (ch == 16)
+            rc = launch_bwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                                dimg, grec, gfeat, 1);
+        else if (ch == 8)
+            rc = launch_bwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                               dimg, grec, gfeat, 1);
+        else
+            rc = launch_bwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
+                               dimg, grec, gfeat, 1);
+        if (rc) return rc;
+        c0 += ch;
+    }
+    return MSB_OK;
+}
+
 }  // namespace msb
 
 using namespace msb;
@@ -485,36 +552,21 @@ int msb_alpha_blending_fwd(const float* uv, const float* conic, const float* opa
         if (rc) return rc;
     }
     const float* fsrc = (C != Cpad) ? featp : feature;
-    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
-    const int2* tr = reinterpret_cast<const int2*>(tile_range);
-    int c0 = 0, first = 1;
-    do {  // at least one pass so that final_T / ncontrib exist even for C == 0
-        const int rem = Cpad - c0;
-        const int ch = C == 0 ? 4 : pick_fwd_ch(rem);
-        const int c_valid = max(0, min(ch, C - c0));
-        float* img = image ? image + (size_t)c0 * H * W : nullptr;
-        int rc;
-        if (C == 0) {  // geometry-only pass: stage rec twice (no feature rows exist)
-            rc = launch_fwd<4>(grid, st, rec, reinterpret_cast<const float*>(rec), 8, 0, idx_sorted, tr, bg, 0, W, H, 1,
-                               final_T, ncontrib, img);
-        } else if (ch == 32) {
-            rc = launch_fwd<32>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img);
-        } else if (ch == 16) {
-            rc = launch_fwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img);
-        } else if (ch == 8) {
-            rc = launch_fwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img);
-        } else {
-            rc = launch_fwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img);
-        }
-        if (rc) return rc;
-        c0 += ch;
-        first = 0;
-    } while (c0 < C);
-    return MSB_OK;
+    return run_fwd_passes(st, rec, fsrc, Cpad, C, idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib);
+}
+
+// Forward on inputs that are already in the packed layout (rec [P,8], featp [P,Cpad] with
+// Cpad = msb_blend_cpad(C)): what msb_render_preprocess_fwd produces.
+int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
+                         float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
+                         void* stream) {
+    // rec / featp may be NULL for an empty cloud (every tile range is then (0, 0))
+    if (C < 0 || W <= 0 || H <= 0 || !tile_range || !final_T || !ncontrib || (C > 0 && !image))
+        return set_error(MSB_ERR_ARG, "blend_packed_fwd: bad argument");
+    if ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(featp)) & 15u)
+        return set_error(MSB_ERR_ARG, "blend_packed_fwd: 16-byte alignment");
+    return run_fwd_passes((cudaStream_t)stream, reinterpret_cast<const float4*>(rec), featp, msb_blend_cpad(C), C,
+                          idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib);
 }
 
 // Backward.  `packed` is the buffer produced by the forward call on the same inputs.
@@ -537,31 +589,31 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
     float* gfeat = grec + (size_t)P * 8;
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)P * (8 + Cpad) * sizeof(float), st);
     if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: memset failed");
-    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
-    const int2* tr = reinterpret_cast<const int2*>(tile_range);
-    for (int c0 = 0; c0 < C;) {
-        const int rem = Cpad - c0;
-        const int ch = pick_bwd_ch(rem);
-        const int c_valid = min(ch, C - c0);
-        const float* dimg = dL_dimage + (size_t)c0 * H * W;
-        int rc;
-        // geometric gradients are linear in the channels: every chunk adds its share (D1 in the
-        // reference does the same, alpha_blending.cu:436-567)
-        if (ch == 16)
-            rc = launch_bwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                                dimg, grec, gfeat, 1);
-        else if (ch == 8)
-            rc = launch_bwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, grec, gfeat, 1);
-        else
-            rc = launch_bwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, grec, gfeat, 1);
-        if (rc) return rc;
-        c0 += ch;
-    }
+    int rc = run_bwd_passes(st, rec, fsrc, Cpad, C, idx_sorted, tile_range, bg, W, H, final_T, ncontrib, dL_dimage, grec,
+                            gfeat);
+    if (rc) return rc;
     blend_unpack_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, C, Cpad, grec, gfeat, dL_duv, dL_dconic,
                                                                     dL_dopacity, dL_dfeature);
     return check_launch("alpha_blending_bwd/unpack");
+}
+
+// Backward on packed inputs; the gradients stay packed: grec [P,8] = {dL_duv.xy, dL_dconic.xyz,
+// dL_dopacity, 0, 0}, gfeat [P,Cpad].  Both are zeroed by this call and consumed by
+// msb_render_preprocess_bwd.
+int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
+                         float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
+                         const float* dL_dimage, float* grec, float* gfeat, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || C < 0 || W <= 0 || H <= 0) return set_error(MSB_ERR_ARG, "blend_packed_bwd: bad argument");
+    if (P == 0) return MSB_OK;
+    if (!rec || !featp || !tile_range || !final_T || !ncontrib || !grec || !gfeat || (C > 0 && !dL_dimage))
+        return set_error(MSB_ERR_ARG, "blend_packed_bwd: null pointer");
+    const int Cpad = msb_blend_cpad(C);
+    cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)P * 8 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gfeat, 0, (size_t)P * Cpad * sizeof(float), st);
+    if (e != cudaSuccess) return set_error((int)e, "blend_packed_bwd: memset failed");
+    return run_bwd_passes(st, reinterpret_cast<const float4*>(rec), featp, Cpad, C, idx_sorted, tile_range, bg, W, H,
+                          final_T, ncontrib, dL_dimage, grec, gfeat);
 }
 
 }  // extern "C"

@@ -20,28 +20,6 @@ namespace msb {
 
 constexpr int NT = 256;
 
-// block-level reduction of 16 camera-gradient partials, then one atomic per value per block
-__device__ __forceinline__ void cam_reduce_atomic(float* cam, float* __restrict__ dL_dintr,
-                                                  float* __restrict__ dL_dextr, float* s_red /*[8][16]*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float v = warp_sum(cam[i]);
-        if (lane == 0) s_red[warp * 16 + i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) v += s_red[w * 16 + threadIdx.x];
-        if (threadIdx.x < 4) {
-            if (dL_dintr != nullptr && v != 0.f) atomicAdd(dL_dintr + threadIdx.x, v);
-        } else {
-            if (dL_dextr != nullptr && v != 0.f) atomicAdd(dL_dextr + (threadIdx.x - 4), v);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // K1  project_point forward
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,573 @@
+// msplat_b200/csrc/render.cu -- fused per-Gaussian preprocess for the SH render path.
+//
+// One forward kernel does what the steps pipeline does in seven launches plus torch glue
+//   project_point  (/root/reference/msplat/src/project_point.cu:13-57)
+//   visible = depth != 0, compute_cov3d (src/compute_cov3d.cu:14-58)
+//   ewa_project    (src/ewa_project.cu:16-83)
+//   view dir = normalize(xyz - camera centre), compute_sh (src/compute_sh.cu:17-503,1600-1637)
+//   colour = clamp_min(sh + 0.5, 0), feature = cat(colour, depth)   (tutorial glue)
+//   + the blend kernels' record packing (blend.cu: blend_pack_kernel)
+// and one backward kernel does the reverse (K8 + glue + K6 + K4 + K2), optionally ACCUMULATING
+// into the gradient tensors so that a batch of views needs no separate add passes.
+//
+// The geometry uses the same device functions as the step kernels (geom.cuh), so uv, depth,
+// conic, radius and tiles are bit-identical to the steps API and to the reference build.
+//
+// Layout / roofline (HBM-bound): a block owns G consecutive Gaussians (G = 256 for degree <= 4).
+//   phase 1  one thread per Gaussian: [G,K] input slabs staged with coalesced 16-byte loads,
+//            geometry + cull extents + SH basis (once per Gaussian, into shared memory [D][G+1]);
+//            Gaussians that touch no tile are dropped here: their SH rows are never read;
+//   phase 2  groups of LPR lanes stream the surviving Gaussians' [Cs, D] coefficient rows with
+//            16-byte loads (sh_layout.cuh), shuffle-reduce, write colours into a shared slab;
+//   phase 3  (backward) one thread per Gaussian: dL_ddir -> dL_dxyz through the normalisation,
+//            projection / EWA / cov3d backward; outputs leave through shared slabs, 16-byte stores.
+// Algorithmic bytes per Gaussian at SH3 RGB+depth: forward 44 + 192*v in, 64 out;
+// backward 44 + 48 + 4 + 192*v in, 48 + 192 out (+ the same again when accumulating),
+// v = fraction of Gaussians that touch a tile.
+#include "blend_math.cuh"
+#include "geom.cuh"
+#include "sh_eval.cuh"
+#include "sh_layout.cuh"
+
+namespace msb {
+
+constexpr int RP_NT = 256;
+__host__ __device__ constexpr int rp_gpb(int deg) { return deg <= 4 ? 256 : deg <= 6 ? 128 : 64; }
+__host__ __device__ constexpr int rp_bs(int deg) { return (sh_dim(deg) * (rp_gpb(deg) + 1) + 3) / 4 * 4; }
+
+constexpr unsigned RP_INVISIBLE = 0x80000000u;  // list flag: Gaussian touches no tile
+constexpr unsigned RP_DEAD = 0x40000000u;       // list flag: no colour gradient arrived
+
+struct CamCenter {
+    float x, y, z;
+};
+// camera centre in world space: -R^T t
+MSB_HD CamCenter cam_center(const Cam& c) {
+    const float* e = c.e;
+    CamCenter o;
+    o.x = -(e[0] * e[3] + e[4] * e[7] + e[8] * e[11]);
+    o.y = -(e[1] * e[3] + e[5] * e[7] + e[9] * e[11]);
+    o.z = -(e[2] * e[3] + e[6] * e[7] + e[10] * e[11]);
+    return o;
+}
+
+// block-wide append of the threads with `flag` set to s_list (order irrelevant)
+__device__ __forceinline__ void list_append(bool flag, unsigned value, unsigned* s_list, int* s_cnt) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(s_cnt, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) s_list[base + __popc(bal & ((1u << lane) - 1u))] = value;
+}
+
+template <int NT>
+__device__ __forceinline__ void slab_store_acc(float* __restrict__ g, const float* __restrict__ smem,
+                                               long long first, int count) {
+    float* dst = g + first;
+    const int nvec = count >> 2;
+    float4* v = reinterpret_cast<float4*>(dst);
+    const float4* s = reinterpret_cast<const float4*>(smem);
+    for (int i = threadIdx.x; i < nvec; i += NT) {
+        float4 a = v[i];
+        const float4 b = s[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        v[i] = a;
+    }
+    for (int i = 4 * nvec + threadIdx.x; i < count; i += NT) dst[i] += smem[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int DEG>
+__global__ void __launch_bounds__(RP_NT) render_pre_fwd_kernel(
+    int P, int Cs, int Cpad, int with_depth, const float* __restrict__ xyz, const float* __restrict__ scale,
+    const float* __restrict__ quat, const float* __restrict__ opacity, const float* __restrict__ shs,
+    const float* __restrict__ intr, const float* __restrict__ extr, int W, int H, float nearest, float extent,
+    float sh_bias, int clamp, float* __restrict__ rec, float* __restrict__ featp, float* __restrict__ uv,
+    float* __restrict__ depth, int* __restrict__ radius, int* __restrict__ tiles) {
+    constexpr int D = sh_dim(DEG);
+    constexpr int G = rp_gpb(DEG);
+    constexpr int GS = G + 1;
+    constexpr bool VEC = sh_vec(DEG);
+    constexpr int LPR = sh_lpr(DEG);
+    constexpr int IT = sh_iters(DEG);
+    constexpr int UNITS = sh_units(DEG);
+    constexpr int WD = VEC ? 4 : 1;
+    constexpr int GROUPS = RP_NT / LPR;
+    extern __shared__ __align__(16) float sm[];
+    float* s_xyz = sm;             // [G,3]   -> reused as the rec slab [G,8] after phase 1
+    float* s_scale = sm + 3 * G;   // [G,3]
+    float* s_quat = sm + 6 * G;    // [G,4]
+    float* s_op = sm + 10 * G;     // [G]
+    float* s_uv = sm + 11 * G;     // [G,2]
+    float* s_B = sm + 13 * G;      // [D][GS]
+    float* s_feat = s_B + rp_bs(DEG);                              // [G,Cpad]
+    unsigned* s_list = reinterpret_cast<unsigned*>(s_feat + (size_t)Cpad * G);  // [G]
+    __shared__ int s_cnt;
+
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * G;
+    const int rows = (int)min((long long)G, (long long)P - g0);
+    const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
+    const Cam c = load_cam(intr, extr);
+    const CamCenter cc = cam_center(c);
+    if (tid == 0) s_cnt = 0;
+    slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+    slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+    slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+    slab_load<RP_NT>(s_op, opacity, g0, rows);
+    __syncthreads();
+
+    // ---- phase 1: geometry + basis, one thread per Gaussian -------------------------------------
+    const int t = tid;
+    float u = 0.f, v = 0.f, d = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f, hx = 0.f, hy = 0.f;
+    int rad = 0, til = 0;
+    if (t < rows) {
+        const float px = s_xyz[3 * t], py = s_xyz[3 * t + 1], pz = s_xyz[3 * t + 2];
+        if (!project_fwd(c, px, py, pz, W, H, nearest, extent, u, v, d)) u = v = d = 0.f;
+        if (d != 0.f) {  // visible = depth != 0 (msplat/__init__.py:73)
+            const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
+            float cv[6];
+            cov3d_fwd(s_scale[3 * t], s_scale[3 * t + 1], s_scale[3 * t + 2], q.x, q.y, q.z, q.w, cv);
+            if (!ewa_fwd(c, px, py, pz, cv, u, v, gx, gy, cx, cy, cz, rad, til)) {
+                cx = cy = cz = 0.f;
+                rad = til = 0;
+            }
+        }
+        op = s_op[t];
+        if (til > 0) {
+            cull_extent(cx, cy, cz, op, hx, hy);
+            const float rx = px - cc.x, ry = py - cc.y, rz = pz - cc.z;
+            const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+            sh_basis<DEG>(rx * inv, ry * inv, rz * inv, s_B + t, GS);
+        }
+    }
+    list_append(til > 0, (unsigned)t, s_list, &s_cnt);
+    __syncthreads();  // every thread is done with the input slabs
+    if (t < rows) {
+        float4* r = reinterpret_cast<float4*>(sm) + 2 * t;
+        r[0] = make_float4(u, v, cx, cy);
+        r[1] = make_float4(cz, op, hx, hy);
+        s_uv[2 * t] = u;
+        s_uv[2 * t + 1] = v;
+        float* f = s_feat + (size_t)t * Cpad;
+        for (int k = 0; k < Cpad; ++k) f[k] = 0.f;
+        if (with_depth) f[Cs] = d;
+        depth[g0 + t] = d;
+        radius[g0 + t] = rad;
+        tiles[g0 + t] = til;
+    }
+    __syncthreads();
+
+    // ---- phase 2: SH rows of the surviving Gaussians, LPR lanes per Gaussian ---------------------
+    const int cnt = s_cnt;
+    const int grp = tid / LPR, s = tid % LPR;
+    for (int k0 = 0; k0 < cnt; k0 += GROUPS) {  // uniform trip count across the block
+        const int k = k0 + grp;
+        const bool act = k < cnt;
+        const int gl = act ? (int)s_list[k] : 0;
+        float b[IT * WD];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int un = s + it * LPR;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) b[it * WD + j] = (act && un < UNITS) ? s_B[(un * WD + j) * GS + gl] : 0.f;
+        }
+        const long long row0 = (g0 + gl) * Cs;
+        for (int ch = 0; ch < Cs; ++ch) {
+            const float* rp = shs + (row0 + ch) * D;
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int un = s + it * LPR;
+                if (VEC) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
+                    acc = fmaf(x.x, b[it * WD + 0], acc);
+                    acc = fmaf(x.y, b[it * WD + (WD > 1 ? 1 : 0)], acc);
+                    acc = fmaf(x.z, b[it * WD + (WD > 2 ? 2 : 0)], acc);
+                    acc = fmaf(x.w, b[it * WD + (WD > 3 ? 3 : 0)], acc);
+                } else {
+                    const float x = (act && un < UNITS) ? __ldg(rp + un) : 0.f;
+                    acc = fmaf(x, b[it * WD], acc);
+                }
+            }
+            acc = group_sum<LPR>(acc);
+            if (act && s == 0) {
+                float val = acc + sh_bias;
+                if (clamp) val = fmaxf(val, 0.f);
+                s_feat[(size_t)gl * Cpad + ch] = val;
+            }
+        }
+    }
+    __syncthreads();
+    slab_store<RP_NT>(rec, sm, g0 * 8, rows * 8);
+    slab_store<RP_NT>(uv, s_uv, g0 * 2, rows * 2);
+    slab_store<RP_NT>(featp, s_feat, g0 * Cpad, rows * Cpad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int DEG, bool CAM>
+__global__ void __launch_bounds__(RP_NT) render_pre_bwd_kernel(
+    int P, int Cs, int Cpad, int with_depth, int accumulate, const float* __restrict__ xyz,
+    const float* __restrict__ scale, const float* __restrict__ quat, const float* __restrict__ shs,
+    const float* __restrict__ intr, const float* __restrict__ extr, float sh_bias, int clamp,
+    const int* __restrict__ tiles, const float* __restrict__ grec, const float* __restrict__ gfeat,
+    float* __restrict__ dL_dxyz, float* __restrict__ dL_dscale, float* __restrict__ dL_dquat,
+    float* __restrict__ dL_dopacity, float* __restrict__ dL_dshs, float* __restrict__ dL_dintr,
+    float* __restrict__ dL_dextr) {
+    constexpr int D = sh_dim(DEG);
+    constexpr int G = rp_gpb(DEG);
+    constexpr int GS = G + 1;
+    constexpr bool VEC = sh_vec(DEG);
+    constexpr int LPR = sh_lpr(DEG);
+    constexpr int IT = sh_iters(DEG);
+    constexpr int UNITS = sh_units(DEG);
+    constexpr int WD = VEC ? 4 : 1;
+    constexpr int GROUPS = RP_NT / LPR;
+    extern __shared__ __align__(16) float sm[];
+    float* s_xyz = sm;             // [G,3]  -> dL_dxyz slab
+    float* s_scale = sm + 3 * G;   // [G,3]  -> dL_dscale slab
+    float* s_quat = sm + 6 * G;    // [G,4]  -> dL_dquat slab
+    float* s_grec = sm + 10 * G;   // [G,8]
+    float* s_B = sm + 18 * G;      // [D][GS]
+    float* s_W = s_B + rp_bs(DEG);  // [D][GS]
+    float* s_gfeat = s_W + rp_bs(DEG);                                            // [G,Cpad]
+    unsigned* s_list = reinterpret_cast<unsigned*>(s_gfeat + (size_t)Cpad * G);   // [G]
+    __shared__ int s_cnt;
+    __shared__ float s_red[8 * 16];
+
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * G;
+    const int rows = (int)min((long long)G, (long long)P - g0);
+    const Cam c = load_cam(intr, extr);
+    const CamCenter cc = cam_center(c);
+    if (tid == 0) s_cnt = 0;
+    slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+    slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+    slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+    slab_load<RP_NT>(s_grec, grec, g0 * 8, rows * 8);
+    slab_load<RP_NT>(s_gfeat, gfeat, g0 * Cpad, rows * Cpad);
+    __syncthreads();
+
+    // ---- phase 1: basis of the Gaussians that received a colour gradient -------------------------
+    const int t = tid;
+    bool vis = false, live = false;
+    float dirx = 0.f, diry = 0.f, dirz = 0.f, inv = 0.f;
+    if (t < rows) {
+        vis = tiles[g0 + t] > 0;
+        if (vis) {
+            const float* gf = s_gfeat + (size_t)t * Cpad;
+            for (int k = 0; k < Cs; ++k) live = live || (gf[k] != 0.f);
+            if (live) {
+                const float rx = s_xyz[3 * t] - cc.x, ry = s_xyz[3 * t + 1] - cc.y, rz = s_xyz[3 * t + 2] - cc.z;
+                inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+                dirx = rx * inv;
+                diry = ry * inv;
+                dirz = rz * inv;
+                sh_basis<DEG>(dirx, diry, dirz, s_B + t, GS);
+            }
+        }
+    }
+    // write mode: every row of dL_dshs must be produced (zeros for untouched Gaussians);
+    // accumulate mode: only rows that actually change are touched
+    const bool listed = accumulate ? live : (t < rows);
+    list_append(listed, (unsigned)t | (vis ? 0u : RP_INVISIBLE) | (live ? 0u : RP_DEAD), s_list, &s_cnt);
+    __syncthreads();
+
+    // ---- phase 2: dL_dshs rows + w_d = sum_c dL_dvalue_c * shs[c, d] ------------------------------
+    const int cnt = s_cnt;
+    const int grp = tid / LPR, s = tid % LPR;
+    for (int k0 = 0; k0 < cnt; k0 += GROUPS) {
+        const int k = k0 + grp;
+        const bool act = k < cnt;
+        const unsigned ent = act ? s_list[k] : (RP_INVISIBLE | RP_DEAD);
+        const int gl = (int)(ent & 0x3fffffffu);
+        const bool lv = act && !(ent & RP_DEAD);
+        float b[IT * WD], wacc[IT * WD];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int un = s + it * LPR;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) {
+                b[it * WD + j] = (lv && un < UNITS) ? s_B[(un * WD + j) * GS + gl] : 0.f;
+                wacc[it * WD + j] = 0.f;
+            }
+        }
+        const long long row0 = (g0 + gl) * Cs;
+        for (int ch = 0; ch < Cs; ++ch) {
+            const float* rp = shs + (row0 + ch) * D;
+            float* op = dL_dshs + (row0 + ch) * D;
+            const float gv = lv ? s_gfeat[(size_t)gl * Cpad + ch] : 0.f;
+            float sv[IT * WD];
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int un = s + it * LPR;
+                if (VEC) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lv && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
+                    sv[it * WD + 0] = x.x;
+                    sv[it * WD + (WD > 1 ? 1 : 0)] = x.y;
+                    sv[it * WD + (WD > 2 ? 2 : 0)] = x.z;
+                    sv[it * WD + (WD > 3 ? 3 : 0)] = x.w;
+                    acc = fmaf(x.x, b[it * WD + 0], acc);
+                    acc = fmaf(x.y, b[it * WD + (WD > 1 ? 1 : 0)], acc);
+                    acc = fmaf(x.z, b[it * WD + (WD > 2 ? 2 : 0)], acc);
+                    acc = fmaf(x.w, b[it * WD + (WD > 3 ? 3 : 0)], acc);
+                } else {
+                    const float x = (lv && un < UNITS) ? __ldg(rp + un) : 0.f;
+                    sv[it * WD] = x;
+                    acc = fmaf(x, b[it * WD], acc);
+                }
+            }
+            // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
+            acc = group_sum<LPR>(acc);
+            const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gv;
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int un = s + it * LPR;
+                if (!(act && un < UNITS)) continue;
+                if (VEC) {
+                    float4 o = make_float4(b[it * WD] * dv, b[it * WD + (WD > 1 ? 1 : 0)] * dv,
+                                           b[it * WD + (WD > 2 ? 2 : 0)] * dv, b[it * WD + (WD > 3 ? 3 : 0)] * dv);
+                    float4* q = reinterpret_cast<float4*>(op) + un;
+                    if (accumulate) {
+                        if (dv != 0.f) {
+                            const float4 old = *q;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            *q = o;
+                        }
+                    } else {
+                        *q = o;
+                    }
+                } else {
+                    const float o = b[it * WD] * dv;
+                    if (accumulate) {
+                        if (dv != 0.f) op[un] += o;
+                    } else {
+                        op[un] = o;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < IT * WD; ++i) wacc[i] = fmaf(sv[i], dv, wacc[i]);
+        }
+        if (lv) {
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int un = s + it * LPR;
+#pragma unroll
+                for (int j = 0; j < WD; ++j)
+                    if (un < UNITS) s_W[(un * WD + j) * GS + gl] = wacc[it * WD + j];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: geometry backward, one thread per Gaussian ------------------------------------
+    float cam[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cam[i] = 0.f;
+    float dx = 0.f, dy = 0.f, dz = 0.f, dop = 0.f;
+    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < rows && vis) {
+        const float px = s_xyz[3 * t], py = s_xyz[3 * t + 1], pz = s_xyz[3 * t + 2];
+        const float4 ga = reinterpret_cast<const float4*>(s_grec)[2 * t];      // dL_duv, dL_dconic.xy
+        const float4 gb = reinterpret_cast<const float4*>(s_grec)[2 * t + 1];  // dL_dconic.z, dL_dopacity
+        dop = gb.y;
+        const float gd = with_depth ? s_gfeat[(size_t)t * Cpad + Cs] : 0.f;
+        project_bwd<CAM>(c, px, py, pz, ga.x, ga.y, gd, dx, dy, dz, cam);
+        const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
+        const float sx = s_scale[3 * t], sy = s_scale[3 * t + 1], sz = s_scale[3 * t + 2];
+        float cv[6], dcv[6], ex, ey, ez;
+        cov3d_fwd(sx, sy, sz, q.x, q.y, q.z, q.w, cv);
+        if (ewa_bwd<CAM>(c, px, py, pz, cv, ga.z, ga.w, gb.x, ex, ey, ez, dcv, cam)) {
+            dx += ex;
+            dy += ey;
+            dz += ez;
+            cov3d_bwd(sx, sy, sz, q.x, q.y, q.z, q.w, dcv, ds, dq);
+        }
+        if (live) {
+            float hx, hy, hz;  // dL_ddir
+            sh_basis_grad<DEG>(dirx, diry, dirz, s_W + t, GS, hx, hy, hz);
+            // dir = r / |r|  =>  dL_dr = (g - dir (dir . g)) / |r|
+            const float dt = dirx * hx + diry * hy + dirz * hz;
+            dx += (hx - dirx * dt) * inv;
+            dy += (hy - diry * dt) * inv;
+            dz += (hz - dirz * dt) * inv;
+        }
+    }
+    __syncthreads();  // (s_xyz/s_scale/s_quat rows are private, but keep the slab hand-over explicit)
+    if (t < rows) {
+        s_xyz[3 * t] = dx;
+        s_xyz[3 * t + 1] = dy;
+        s_xyz[3 * t + 2] = dz;
+        s_scale[3 * t] = ds[0];
+        s_scale[3 * t + 1] = ds[1];
+        s_scale[3 * t + 2] = ds[2];
+        reinterpret_cast<float4*>(s_quat)[t] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        if (accumulate) {
+            if (dop != 0.f) dL_dopacity[g0 + t] += dop;
+        } else {
+            dL_dopacity[g0 + t] = dop;
+        }
+    }
+    __syncthreads();
+    if (accumulate) {
+        slab_store_acc<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+        slab_store_acc<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+        slab_store_acc<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+    } else {
+        slab_store<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+        slab_store<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+        slab_store<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+    }
+    if (CAM) cam_reduce_atomic<RP_NT>(cam, dL_dintr, dL_dextr, s_red);
+}
+
+static size_t rp_smem_fwd(int deg, int Cpad) {
+    const int G = rp_gpb(deg);
+    return ((size_t)13 * G + rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
+}
+static size_t rp_smem_bwd(int deg, int Cpad) {
+    const int G = rp_gpb(deg);
+    return ((size_t)18 * G + 2 * (size_t)rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
+}
+
+struct RpFwdArgs {
+    int P, Cs, Cpad, with_depth;
+    const float *xyz, *scale, *quat, *opacity, *shs, *intr, *extr;
+    int W, H;
+    float nearest, extent, sh_bias;
+    int clamp;
+    float *rec, *featp, *uv, *depth;
+    int *radius, *tiles;
+};
+
+template <int DEG>
+static int rp_launch_fwd(const RpFwdArgs& a, cudaStream_t st) {
+    const size_t smem = rp_smem_fwd(DEG, a.Cpad);
+    if (smem > 200 * 1024) return set_error(MSB_ERR_RANGE, "render_preprocess_fwd: too many channels for shared memory");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(render_pre_fwd_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: cudaFuncSetAttribute failed");
+    }
+    const int G = rp_gpb(DEG);
+    const unsigned grid = (unsigned)(((long long)a.P + G - 1) / G);
+    render_pre_fwd_kernel<DEG><<<grid, RP_NT, smem, st>>>(a.P, a.Cs, a.Cpad, a.with_depth, a.xyz, a.scale, a.quat,
+                                                          a.opacity, a.shs, a.intr, a.extr, a.W, a.H, a.nearest,
+                                                          a.extent, a.sh_bias, a.clamp, a.rec, a.featp, a.uv, a.depth,
+                                                          a.radius, a.tiles);
+    return check_launch("render_preprocess_fwd");
+}
+
+struct RpBwdArgs {
+    int P, Cs, Cpad, with_depth, accumulate;
+    const float *xyz, *scale, *quat, *shs, *intr, *extr;
+    float sh_bias;
+    int clamp;
+    const int* tiles;
+    const float *grec, *gfeat;
+    float *dxyz, *dscale, *dquat, *dopacity, *dshs, *dintr, *dextr;
+};
+
+template <int DEG, bool CAM>
+static int rp_launch_bwd(const RpBwdArgs& a, cudaStream_t st) {
+    const size_t smem = rp_smem_bwd(DEG, a.Cpad);
+    if (smem > 200 * 1024) return set_error(MSB_ERR_RANGE, "render_preprocess_bwd: too many channels for shared memory");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(render_pre_bwd_kernel<DEG, CAM>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "render_preprocess_bwd: cudaFuncSetAttribute failed");
+    }
+    const int G = rp_gpb(DEG);
+    const unsigned grid = (unsigned)(((long long)a.P + G - 1) / G);
+    render_pre_bwd_kernel<DEG, CAM><<<grid, RP_NT, smem, st>>>(
+        a.P, a.Cs, a.Cpad, a.with_depth, a.accumulate, a.xyz, a.scale, a.quat, a.shs, a.intr, a.extr, a.sh_bias,
+        a.clamp, a.tiles, a.grec, a.gfeat, a.dxyz, a.dscale, a.dquat, a.dopacity, a.dshs, a.dintr, a.dextr);
+    return check_launch("render_preprocess_bwd");
+}
+
+static inline bool rp_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int msb_blend_cpad(int C);
+
+// Fused forward preprocess of the SH render path.  Outputs: rec [P,8] and featp [P,Cpad]
+// (Cpad = msb_blend_cpad(Cs + with_depth)) in the blend kernels' packed layout, uv [P,2],
+// depth [P], radius [P], tiles [P] (bit-identical to project_point / ewa_project).
+int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* opacity,
+                              const float* shs, const float* intr, const float* extr, int P, int Cs, int D,
+                              int with_depth, int W, int H, float nearest, float extent, float sh_bias, int clamp,
+                              float* rec, float* featp, float* uv, float* depth, int32_t* radius, int32_t* tiles,
+                              void* stream) {
+    if (P == 0) return MSB_OK;
+    const int deg = sh_degree_of(D);
+    if (P < 0 || Cs < 0 || deg < 0 || W <= 0 || H <= 0)
+        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: bad size (D must be (deg+1)^2, deg <= 10)");
+    if (!xyz || !scale || !quat || !opacity || (Cs > 0 && !shs) || !intr || !extr || !rec || !featp || !uv || !depth ||
+        !radius || !tiles)
+        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: null pointer");
+    if (!(rp_al16(xyz) && rp_al16(scale) && rp_al16(quat) && rp_al16(opacity) && rp_al16(shs) && rp_al16(rec) &&
+          rp_al16(featp) && rp_al16(uv)))
+        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: 16-byte alignment");
+    RpFwdArgs a{P, Cs, msb_blend_cpad(Cs + (with_depth ? 1 : 0)), with_depth ? 1 : 0, xyz, scale, quat, opacity, shs,
+                intr, extr, W, H, nearest, extent, sh_bias, clamp ? 1 : 0, rec, featp, uv, depth, radius, tiles};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (deg) {
+#define MSB_RP_CASE(d) \
+    case d:            \
+        return rp_launch_fwd<d>(a, st);
+        MSB_RP_CASE(0) MSB_RP_CASE(1) MSB_RP_CASE(2) MSB_RP_CASE(3) MSB_RP_CASE(4) MSB_RP_CASE(5)
+        MSB_RP_CASE(6) MSB_RP_CASE(7) MSB_RP_CASE(8) MSB_RP_CASE(9) MSB_RP_CASE(10)
+#undef MSB_RP_CASE
+    }
+    return set_error(MSB_ERR_ARG, "render_preprocess_fwd: unsupported degree");
+}
+
+// Fused backward.  grec [P,8] = {dL_duv.xy, dL_dconic.xyz, dL_dopacity, -, -} and gfeat [P,Cpad]
+// are the packed gradients written by msb_blend_packed_bwd.  accumulate != 0: outputs are
+// added to (view batches); otherwise every output element is written.  dL_dintr [4] /
+// dL_dextr [12] may be NULL; otherwise they are accumulated into.
+int msb_render_preprocess_bwd(const float* xyz, const float* scale, const float* quat, const float* shs,
+                              const float* intr, const float* extr, const int32_t* tiles, const float* grec,
+                              const float* gfeat, int P, int Cs, int D, int with_depth, float sh_bias, int clamp,
+                              int accumulate, float* dL_dxyz, float* dL_dscale, float* dL_dquat, float* dL_dopacity,
+                              float* dL_dshs, float* dL_dintr, float* dL_dextr, void* stream) {
+    if (P == 0) return MSB_OK;
+    const int deg = sh_degree_of(D);
+    if (P < 0 || Cs < 0 || deg < 0) return set_error(MSB_ERR_ARG, "render_preprocess_bwd: bad size");
+    if (!xyz || !scale || !quat || (Cs > 0 && (!shs || !dL_dshs)) || !intr || !extr || !tiles || !grec || !gfeat ||
+        !dL_dxyz || !dL_dscale || !dL_dquat || !dL_dopacity)
+        return set_error(MSB_ERR_ARG, "render_preprocess_bwd: null pointer");
+    if (!(rp_al16(xyz) && rp_al16(scale) && rp_al16(quat) && rp_al16(shs) && rp_al16(grec) && rp_al16(gfeat) &&
+          rp_al16(dL_dxyz) && rp_al16(dL_dscale) && rp_al16(dL_dquat) && rp_al16(dL_dshs)))
+        return set_error(MSB_ERR_ARG, "render_preprocess_bwd: 16-byte alignment");
+    RpBwdArgs a{P, Cs, msb_blend_cpad(Cs + (with_depth ? 1 : 0)), with_depth ? 1 : 0, accumulate ? 1 : 0, xyz, scale,
+                quat, shs, intr, extr, sh_bias, clamp ? 1 : 0, tiles, grec, gfeat, dL_dxyz, dL_dscale, dL_dquat,
+                dL_dopacity, dL_dshs, dL_dintr, dL_dextr};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool camg = dL_dintr || dL_dextr;
+    switch (deg) {
+#define MSB_RP_CASE(d) \
+    case d:            \
+        return camg ? rp_launch_bwd<d, true>(a, st) : rp_launch_bwd<d, false>(a, st);
+        MSB_RP_CASE(0) MSB_RP_CASE(1) MSB_RP_CASE(2) MSB_RP_CASE(3) MSB_RP_CASE(4) MSB_RP_CASE(5)
+        MSB_RP_CASE(6) MSB_RP_CASE(7) MSB_RP_CASE(8) MSB_RP_CASE(9) MSB_RP_CASE(10)
+#undef MSB_RP_CASE
+    }
+    return set_error(MSB_ERR_ARG, "render_preprocess_bwd: unsupported degree");
+}
+
+}  // extern "C"

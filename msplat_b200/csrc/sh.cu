@@ -17,28 +17,11 @@
 // HBM-bound for deg <= 3 (4*Cs*D bytes per Gaussian each way); all indexing is 64-bit
 // (shs[1M,32,121] has 3.9e9 elements).
 #include "sh_eval.cuh"
+#include "sh_layout.cuh"
 
 namespace msb {
 
 constexpr int SH_NT = 256;
-
-__host__ __device__ constexpr int sh_dim(int deg) { return (deg + 1) * (deg + 1); }
-__host__ __device__ constexpr bool sh_vec(int deg) { return sh_dim(deg) % 4 == 0; }
-// lanes per row
-__host__ __device__ constexpr int sh_lpr(int deg) {
-    return deg == 0 ? 1 : deg == 1 ? 1 : deg == 2 ? 4 : deg == 3 ? 4 : deg == 4 ? 8 : deg == 5 ? 4 :
-           deg == 6 ? 16 : deg == 7 ? 16 : deg == 8 ? 32 : deg == 9 ? 8 : 32;
-}
-// units (float4 or float) per row and iterations per lane
-__host__ __device__ constexpr int sh_units(int deg) { return sh_vec(deg) ? sh_dim(deg) / 4 : sh_dim(deg); }
-__host__ __device__ constexpr int sh_iters(int deg) { return (sh_units(deg) + sh_lpr(deg) - 1) / sh_lpr(deg); }
-
-template <int LPR>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 template <int DEG, bool BWD>
 __global__ void __launch_bounds__(SH_NT) sh_kernel(int P, int Cs, int GPB, const float* __restrict__ shs,
@@ -204,12 +187,6 @@ static int sh_dispatch(int deg, int P, int Cs, const float* shs, const float* di
     return set_error(MSB_ERR_ARG, "compute_sh: D must be (deg+1)^2 with 0 <= deg <= 10");
 }
 
-static int sh_degree(int D) {
-    for (int d = 0; d <= 10; ++d)
-        if ((d + 1) * (d + 1) == D) return d;
-    return -1;
-}
-
 }  // namespace msb
 
 using namespace msb;
@@ -221,7 +198,7 @@ int msb_compute_sh_fwd(const float* shs, const float* dirs, const uint8_t* visib
     if (P == 0 || Cs == 0) return MSB_OK;
     if (!(P > 0 && Cs > 0 && shs && dirs && value)) return set_error(MSB_ERR_ARG, "compute_sh_fwd: bad argument");
     if ((reinterpret_cast<uintptr_t>(shs) & 15u) != 0) return set_error(MSB_ERR_ARG, "compute_sh_fwd: shs alignment");
-    return sh_dispatch<false>(sh_degree(D), P, Cs, shs, dirs, visible, nullptr, value, nullptr, nullptr,
+    return sh_dispatch<false>(sh_degree_of(D), P, Cs, shs, dirs, visible, nullptr, value, nullptr, nullptr,
                               (cudaStream_t)stream);
 }
 
@@ -232,7 +209,7 @@ int msb_compute_sh_bwd(const float* shs, const float* dirs, const uint8_t* visib
         return set_error(MSB_ERR_ARG, "compute_sh_bwd: bad argument");
     if (((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dshs)) & 15u) != 0)
         return set_error(MSB_ERR_ARG, "compute_sh_bwd: shs/dL_dshs alignment");
-    return sh_dispatch<true>(sh_degree(D), P, Cs, shs, dirs, visible, dL_dvalue, nullptr, dL_dshs, dL_ddirs,
+    return sh_dispatch<true>(sh_degree_of(D), P, Cs, shs, dirs, visible, dL_dvalue, nullptr, dL_dshs, dL_ddirs,
                              (cudaStream_t)stream);
 }
 

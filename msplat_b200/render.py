@@ -1,0 +1,173 @@
+"""Fused SH render path: ``rasterization_sh`` (one camera) and ``rasterization_sh_views`` (a batch
+of cameras over the same Gaussians).
+
+The reference only offers this as a chain of steps plus torch glue
+(/root/reference/msplat/__init__.py:70-93 preceded by ``compute_sh``; tutorials/gs_3d.py-style):
+
+    uv, depth = project_point(xyz, intr, extr, W, H);  visible = depth != 0
+    dirs = normalize(xyz - camera_centre);  rgb = clamp_min(compute_sh(shs, dirs, visible) + 0.5, 0)
+    feature = cat(rgb, depth) [optional];  cov3d = compute_cov3d(...);  conic, radius, tiles = ewa_project(...)
+    ids, tile_range = sort_gaussian(...);  image = alpha_blending(...)
+
+Here the whole per-Gaussian part is ONE forward and ONE backward kernel (csrc/render.cu) that read
+the parameters once, never materialise cov3d / dirs / rgb and write straight into the blend
+kernels' packed layout; sort and blend are the same kernels as the steps API.  uv, depth, radius,
+tiles, idx_sorted and tile_range are bit-identical to the steps pipeline; images agree to FP32
+rounding of the view-direction normalisation (tests/test_gpu_parity.py::test_render_sh_*).
+
+A view batch shares one host sync (all M read-backs at once) and accumulates the per-Gaussian
+gradients of its views inside the backward kernel (no per-view add passes): SURVEY 8f ranks 1+3.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import as_f32, ptr
+
+__all__ = ["rasterization_sh", "rasterization_sh_views"]
+
+
+def rasterization_sh(
+    xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intr: Tensor, extr: Tensor,
+    W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
+    nearest: float = 0.0, extent: float = 1.3,
+) -> Tensor:
+    """One camera.  xyz [P,3], scale [P,3], rotate [P,4] (r,x,y,z; not normalised inside),
+    opacity [P,1], shs [P,Cs,D] with D=(deg+1)^2, intr [4], extr [3,4]|[4,4] -> image [C,H,W],
+    C = Cs (+1 depth channel if ``with_depth``)."""
+    return rasterization_sh_views(xyz, scale, rotate, opacity, shs, intr[None], extr[None], W, H, bg, sh_bias=sh_bias,
+                                  clamp=clamp, with_depth=with_depth, nearest=nearest, extent=extent)[0]
+
+
+def rasterization_sh_views(
+    xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
+    W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
+    nearest: float = 0.0, extent: float = 1.3,
+) -> Tensor:
+    """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
+    -> images [B,C,H,W]."""
+    if intrs.dim() == 1:
+        intrs = intrs[None].expand(extrs.shape[0], 4)
+    return _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
+                                float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent))
+
+
+class _RenderSHViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scale, rotate, opacity, shs, intrs, extrs, W, H, bg, sh_bias, clamp, with_depth, nearest,
+                extent):
+        x, s, q = as_f32(xyz, "xyz"), as_f32(scale, "scale"), as_f32(rotate, "rotate")
+        o, sh = as_f32(opacity, "opacity"), as_f32(shs, "shs")
+        I, E = as_f32(intrs, "intrs"), as_f32(extrs, "extrs")
+        P = x.shape[0]
+        if x.shape != (P, 3) or s.shape != (P, 3) or q.shape != (P, 4) or o.numel() != P or sh.dim() != 3 \
+                or sh.shape[0] != P:
+            raise RuntimeError("rasterization_sh: xyz [P,3], scale [P,3], rotate [P,4], opacity [P,1], shs [P,Cs,D]")
+        Cs, D = int(sh.shape[1]), int(sh.shape[2])
+        deg = int(round(D ** 0.5)) - 1
+        if (deg + 1) ** 2 != D or not 0 <= deg <= 10:
+            raise RuntimeError(f"shs last dim must be (deg+1)^2 with deg <= 10, got {D}")
+        if E.dim() != 3 or E.shape[1] not in (3, 4) or E.shape[2] != 4 or I.shape != (E.shape[0], 4):
+            raise RuntimeError("rasterization_sh_views: intrs [B,4], extrs [B,3,4] or [B,4,4]")
+        B = E.shape[0]
+        C = Cs + (1 if with_depth else 0)
+        dev = x.device
+        L = _lib.lib()
+        cpad = L.msb_blend_cpad(C)
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        f32, i32 = torch.float32, torch.int32
+        images = torch.empty((B, C, H, W), dtype=f32, device=dev)
+        views = []
+        with torch.cuda.device(dev):
+            totals = _lib.pinned_i64(dev, B)
+            # phase A: per-Gaussian preprocess + tile-count scan of every view, then ONE host sync
+            for b in range(B):
+                rec = torch.empty((P, 8), dtype=f32, device=dev)
+                featp = torch.empty((P, cpad), dtype=f32, device=dev)
+                uv = torch.empty((P, 2), dtype=f32, device=dev)
+                depth = torch.empty((P,), dtype=f32, device=dev)
+                radius = torch.empty((P,), dtype=i32, device=dev)
+                tiles = torch.empty((P,), dtype=i32, device=dev)
+                offsets = torch.empty((P,), dtype=i32, device=dev)
+                _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd, dev, ptr(x), ptr(s),
+                          ptr(q), ptr(o), ptr(sh), ptr(I[b]), ptr(E[b]), P, Cs, D, int(with_depth), W, H, nearest,
+                          extent, sh_bias, int(clamp), ptr(rec), ptr(featp), ptr(uv), ptr(depth), ptr(radius),
+                          ptr(tiles))
+                ws1 = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
+                _lib.call("sort_scan", 3 if P else 0, L.msb_sort_scan, dev, ptr(tiles), P, ptr(offsets),
+                          ptr(totals[b:]), ptr(ws1), ws1.numel())
+                views.append([rec, featp, uv, depth, radius, tiles, offsets])
+            torch.cuda.current_stream(dev).synchronize()
+            Ms = [int(totals[b]) for b in range(B)]
+            # phase B: sort + blend per view
+            saved = []
+            for b in range(B):
+                rec, featp, uv, depth, radius, tiles, offsets = views[b]
+                M = Ms[b]
+                if M >= 2 ** 30:
+                    raise RuntimeError(f"rasterization_sh: {M} tile intersections exceed the supported 2^30")
+                ids = torch.empty((M,), dtype=i32, device=dev)
+                tr = torch.empty((T, 2), dtype=i32, device=dev)
+                ws2 = torch.empty((L.msb_sort_workspace_bytes(M, W, H),), dtype=torch.uint8, device=dev)
+                nk = 2 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
+                _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius), ptr(tiles),
+                          ptr(offsets), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
+                final_T = torch.empty((H, W), dtype=f32, device=dev)
+                ncontrib = torch.empty((H, W), dtype=i32, device=dev)
+                _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd, dev, ptr(rec), ptr(featp),
+                          ptr(ids), ptr(tr), bg, C, W, H, ptr(images[b]), ptr(final_T), ptr(ncontrib))
+                saved += [rec, featp, tiles, ids, tr, final_T, ncontrib]
+                views[b] = None
+        ctx.cfg = (B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth)
+        ctx.cam_grad = (intrs.requires_grad, extrs.requires_grad)
+        ctx.shapes = (tuple(opacity.shape), tuple(intrs.shape), tuple(extrs.shape))
+        ctx.save_for_backward(x, s, q, sh, I, E, *saved)
+        return images
+
+    @staticmethod
+    def backward(ctx, dL_dimages):
+        B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth = ctx.cfg
+        x, s, q, sh, I, E = ctx.saved_tensors[:6]
+        saved = ctx.saved_tensors[6:]
+        g = as_f32(dL_dimages, "dL_dimages")
+        dev = x.device
+        L = _lib.lib()
+        f32 = torch.float32
+        dxyz = torch.empty((P, 3), dtype=f32, device=dev)
+        dscale = torch.empty((P, 3), dtype=f32, device=dev)
+        dquat = torch.empty((P, 4), dtype=f32, device=dev)
+        dop = torch.empty((P,), dtype=f32, device=dev)
+        dshs = torch.empty_like(sh)
+        need_i, need_e = ctx.cam_grad
+        dintr = torch.zeros((B, 4), dtype=f32, device=dev) if need_i else None
+        dextr = torch.zeros((B,) + tuple(E.shape[1:]), dtype=f32, device=dev) if need_e else None
+        if P == 0 or C == 0:
+            for t in (dxyz, dscale, dquat, dop, dshs):
+                t.zero_()
+        else:
+            grec = torch.empty((P, 8), dtype=f32, device=dev)
+            gfeat = torch.empty((P, cpad), dtype=f32, device=dev)
+            for b in range(B):
+                rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
+                _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
+                          ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
+                          ptr(grec), ptr(gfeat))
+                _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x), ptr(s), ptr(q),
+                          ptr(sh), ptr(I[b]), ptr(E[b]), ptr(tiles), ptr(grec), ptr(gfeat), P, Cs, D, int(with_depth),
+                          sh_bias, int(clamp), 1 if b > 0 else 0, ptr(dxyz), ptr(dscale), ptr(dquat), ptr(dop),
+                          ptr(dshs), ptr(dintr[b]) if need_i else None, ptr(dextr[b]) if need_e else None)
+        op_shape = ctx.shapes[0]
+        return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr, dextr, None, None, None, None, None, None,
+                None, None)
+
+
+def _blend_passes_fwd(cpad: int, C: int) -> int:
+    return 1 if C == 0 else (cpad // 32 + (1 if cpad % 32 else 0))
+
+
+def _blend_passes_bwd(cpad: int) -> int:
+    return (cpad + 15) // 16 if cpad > 8 else 1

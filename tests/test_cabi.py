@@ -21,8 +21,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_public_api_names_match_reference():
     # /root/reference/msplat/__init__.py:11-19
-    assert set(msplat_b200.__all__) == {"project_point", "compute_cov3d", "ewa_project", "sort_gaussian",
-                                        "compute_sh", "alpha_blending", "rasterization"}
+    ref_names = {"project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "compute_sh", "alpha_blending",
+                 "rasterization"}
+    assert ref_names <= set(msplat_b200.__all__)
+    assert set(msplat_b200.__all__) - ref_names == {"rasterization_sh", "rasterization_sh_views"}  # extensions
     import inspect
     sig = inspect.signature(msplat_b200.project_point)
     assert list(sig.parameters) == ["xyz", "intr", "extr", "W", "H", "nearest", "extent"]

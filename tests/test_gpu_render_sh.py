@@ -1,0 +1,202 @@
+"""GPU parity of the fused SH render path (msplat_b200.rasterization_sh / rasterization_sh_views,
+csrc/render.cu) against (1) our own steps pipeline, (2) the CPU oracle, (3) the unmodified
+reference CUDA build driven through ITS steps API (the only way the reference renders SH colours).
+
+Bars: images max abs 1e-4 (north star); fused-vs-steps of our own library is held to 2e-6 because
+both run the same geometry/sort/blend code and differ only by the FP32 rounding of the view
+direction normalisation (2e-5 above degree 4); gradients |d| <= rel |g| + eps max|g|.
+"""
+import math
+import os
+
+import pytest
+import torch
+
+import oracle
+from conftest import ROOT
+from test_gpu_parity import DEV, camera, cloud, cpu, grad_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import msplat_b200
+    return msplat_b200
+
+
+def cam_center(extr):
+    R, t = extr[:3, :3], extr[:3, 3]
+    return -(R.T @ t)
+
+
+def steps_pipeline(api, leaves, intr, extr, W, H, bg, with_depth, clamp=True, bias=0.5):
+    """The chain a user of the reference writes (bench.render_once without the loss)."""
+    xyz, scale, quat, opacity, shs = leaves
+    uv, depth = api.project_point(xyz, intr, extr, W, H)
+    visible = depth != 0
+    dirs = xyz - cam_center(extr.detach())
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    rgb = api.compute_sh(shs, dirs, visible.squeeze(-1)) + bias
+    if clamp:
+        rgb = torch.clamp_min(rgb, 0.0)
+    feature = torch.cat([rgb, depth], dim=-1) if with_depth else rgb
+    cov3d = api.compute_cov3d(scale, quat, visible if api is not oracle else visible.reshape(-1))
+    conic, radius, tiles = api.ewa_project(xyz, cov3d, intr, extr, uv, W, H,
+                                           visible if api is not oracle else visible.reshape(-1))
+    ids, tr = api.sort_gaussian(uv, depth, W, H, radius, tiles)
+    return api.alpha_blending(uv, conic, opacity, feature, ids, tr, bg, W, H)
+
+
+def make_leaves(P, Cs, deg, seed, dev):
+    xyz, scale, quat, opacity = cloud(P, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    D = (deg + 1) ** 2
+    shs = torch.randn(P, Cs, D, generator=g) * 0.2
+    shs[:, :, 0] += 0.3 * torch.randn(P, Cs, generator=g)
+    return [t.to(dev).requires_grad_() for t in (xyz, scale, quat, opacity, shs)]
+
+
+@pytest.mark.parametrize("deg,Cs,with_depth,clamp", [(0, 3, False, True), (1, 3, True, True), (2, 3, True, False),
+                                                     (3, 3, True, True), (3, 1, False, True), (4, 5, True, True),
+                                                     (5, 3, False, True), (7, 2, True, True), (10, 3, True, True),
+                                                     (3, 16, True, True)])
+def test_render_sh_equals_steps(ms, deg, Cs, with_depth, clamp):
+    P, W, H, bg = 9001, 320, 200, 0.25
+    intr, extr = camera(W, H)
+    intr, extr = intr.to(DEV), extr.to(DEV)
+    A = make_leaves(P, Cs, deg, 60 + deg, DEV)
+    B = make_leaves(P, Cs, deg, 60 + deg, DEV)
+    img_f = ms.rasterization_sh(*A, intr, extr, W, H, bg, with_depth=with_depth, clamp=clamp)
+    img_s = steps_pipeline(ms, B, intr, extr, W, H, bg, with_depth, clamp)
+    C = Cs + int(with_depth)
+    assert img_f.shape == (C, H, W)
+    err = float((img_f.detach() - img_s.detach()).abs().max())
+    # high degrees amplify the 1-ulp difference of the normalised view direction (Y_10 ~ dir^10)
+    bar = (2e-6 if deg <= 4 else 2e-5) * max(1.0, float(img_s.detach().abs().max()))
+    assert err <= bar, f"fused vs steps image error {err}"
+    g = torch.randn(C, H, W, generator=torch.Generator().manual_seed(5)).to(DEV)
+    (img_f * g).sum().backward()
+    (img_s * g).sum().backward()
+    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B):
+        grad_close(a.grad, b.grad, rel=2e-3, eps=2e-4, what=f"fused vs steps d{n} (deg {deg})")
+
+
+def test_render_sh_camera_grads_and_44_extr(ms):
+    P, W, H, bg, deg, Cs = 7000, 256, 192, 0.0, 2, 3
+    intr, extr = camera(W, H)
+    e44 = torch.cat([extr, torch.tensor([[0.0, 0, 0, 1]])], 0)
+    A = make_leaves(P, Cs, deg, 71, DEV)
+    B = make_leaves(P, Cs, deg, 71, DEV)
+    i1, e1 = intr.to(DEV).requires_grad_(), e44.to(DEV).requires_grad_()
+    i2, e2 = intr.to(DEV).requires_grad_(), extr.to(DEV).requires_grad_()
+    img_f = ms.rasterization_sh(*A, i1, e1, W, H, bg, with_depth=True)
+    img_s = steps_pipeline(ms, B, i2, e2, W, H, bg, True)
+    g = torch.randn(Cs + 1, H, W, generator=torch.Generator().manual_seed(6)).to(DEV)
+    (img_f * g).sum().backward()
+    (img_s * g).sum().backward()
+    assert e1.grad.shape == (4, 4) and float(e1.grad[3].abs().max()) == 0.0
+    grad_close(i1.grad, i2.grad, rel=3e-3, eps=3e-4, what="dL_dintr")
+    grad_close(e1.grad[:3], e2.grad, rel=3e-3, eps=3e-4, what="dL_dextr")
+    grad_close(A[0].grad, B[0].grad, rel=2e-3, eps=2e-4, what="dL_dxyz")
+
+
+def test_render_sh_views_equals_single_views(ms):
+    P, W, H, bg, deg, Cs, nv = 12000, 288, 176, 0.1, 3, 3, 3
+    intr, extr = camera(W, H)
+    extrs = []
+    for k in range(nv):
+        th = 0.15 * (k - 1)
+        Ry = torch.tensor([[math.cos(th), 0, math.sin(th)], [0, 1, 0], [-math.sin(th), 0, math.cos(th)]])
+        e = extr.clone()
+        e[:3, :3] = extr[:3, :3] @ Ry
+        e[0, 3] += 0.2 * k
+        extrs.append(e)
+    extrs = torch.stack(extrs).to(DEV)
+    intrs = intr.to(DEV)[None].repeat(nv, 1)
+    A = make_leaves(P, Cs, deg, 80, DEV)
+    B = make_leaves(P, Cs, deg, 80, DEV)
+    ia, ea = intrs.clone().requires_grad_(), extrs.clone().requires_grad_()
+    ib, eb = intrs.clone().requires_grad_(), extrs.clone().requires_grad_()
+    imgs = ms.rasterization_sh_views(*A, ia, ea, W, H, bg, with_depth=True)
+    assert imgs.shape == (nv, Cs + 1, H, W)
+    g = torch.randn(nv, Cs + 1, H, W, generator=torch.Generator().manual_seed(8)).to(DEV)
+    (imgs * g).sum().backward()
+    for k in range(nv):
+        img = ms.rasterization_sh(*B, ib[k], eb[k], W, H, bg, with_depth=True)
+        assert torch.equal(img, imgs[k]), "a view of the batch must equal the single-view render bit for bit"
+        (img * g[k]).sum().backward()
+    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B):
+        grad_close(a.grad, b.grad, rel=1e-3, eps=1e-4, what=f"view batch d{n}")
+    grad_close(ia.grad, ib.grad, rel=2e-3, eps=2e-4, what="view batch dintr")
+    grad_close(ea.grad, eb.grad, rel=2e-3, eps=2e-4, what="view batch dextr")
+    # shared intrinsics [4] broadcast over the batch
+    i4 = intr.to(DEV).requires_grad_()
+    imgs2 = ms.rasterization_sh_views(*[t.detach() for t in A], i4, extrs, W, H, bg, with_depth=True)
+    assert torch.equal(imgs2, imgs)
+    (imgs2 * g).sum().backward()
+    grad_close(i4.grad, ia.grad.sum(0), rel=2e-3, eps=2e-4, what="shared dintr")
+
+
+def test_render_sh_vs_oracle(ms):
+    P, W, H, bg, deg, Cs = 5000, 200, 120, 0.0, 3, 3
+    intr, extr = camera(W, H)
+    A = make_leaves(P, Cs, deg, 90, DEV)
+    O = make_leaves(P, Cs, deg, 90, "cpu")
+    img = ms.rasterization_sh(*A, intr.to(DEV), extr.to(DEV), W, H, bg, with_depth=True)
+    img_o = steps_pipeline(oracle, O, intr, extr, W, H, bg, True)
+    err = (cpu(img) - img_o.detach()).abs()
+    # depth channel values are O(4): scale the bar by the channel magnitude
+    bar = 1e-4 * max(1.0, float(img_o.abs().max()))
+    assert float(err.max()) <= bar or int((err.amax(0) > bar).sum()) <= 5, f"image err {float(err.max())}"
+    g = torch.randn(Cs + 1, H, W, generator=torch.Generator().manual_seed(9))
+    (img * g.to(DEV)).sum().backward()
+    (img_o * g).sum().backward()
+    if float(err.max()) <= bar:
+        for n, a, o in zip(["xyz", "scale", "quat", "opacity", "shs"], A, O):
+            grad_close(a.grad, o.grad, rel=5e-3, eps=5e-4, what=f"vs oracle d{n}")
+
+
+def test_render_sh_vs_reference_steps(ms, ref_msplat):
+    """The headline comparison of bench.py at a size that runs in seconds: fused path of ours vs
+    the reference's steps API on the same 200k-Gaussian 720p SH3 RGB+depth scene."""
+    from msplat_b200.scenes import frustum_scene
+    sc = frustum_scene(200000, 1280, 720, 2.0, seed=4, sh_degree=3).to(DEV)
+    mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
+    A, B = mk(), mk()
+    img = ms.rasterization_sh(*A, sc.intr, sc.extr, sc.W, sc.H, 0.0, with_depth=True)
+    img_r = steps_pipeline(ref_msplat, B, sc.intr, sc.extr, sc.W, sc.H, 0.0, True)
+    scale = max(1.0, float(img_r.abs().max()))
+    err = float((img - img_r).abs().max())
+    assert err <= 1e-4 * scale, f"image max abs error vs reference {err} (scale {scale})"
+    g = torch.randn(4, sc.H, sc.W, device=DEV)
+    (img * g).sum().backward()
+    (img_r * g).sum().backward()
+    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B):
+        grad_close(a.grad, b.grad, rel=5e-3, eps=5e-4, what=f"d{n} vs reference steps")
+    import json
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"max_abs": err, "scale": scale}, open(os.path.join(ROOT, "gpurun_out", "render_sh_vs_ref.json"), "w"))
+
+
+def test_render_sh_edge_cases(ms):
+    intr, extr = camera(64, 48)
+    intr, extr = intr.to(DEV), extr.to(DEV)
+    # empty cloud
+    z = lambda *s: torch.zeros(*s, device=DEV, requires_grad=True)
+    img = ms.rasterization_sh(z(0, 3), z(0, 3), z(0, 4), z(0, 1), z(0, 3, 16), intr, extr, 64, 48, 0.7)
+    assert img.shape == (3, 48, 64) and bool((img == 0.7).all())
+    img.sum().backward()
+    # every Gaussian behind / outside the frustum: background only, zero gradients
+    A = make_leaves(300, 3, 3, 95, DEV)
+    with torch.no_grad():
+        A[0][:, 2] -= 100.0
+    img = ms.rasterization_sh(*A, intr, extr, 64, 48, 0.2, extent=1.3, nearest=0.1)
+    assert bool((img == 0.2).all())
+    img.sum().backward()
+    assert all(float(a.grad.abs().max()) == 0.0 for a in A)
+    # bad shapes / CPU tensors fail loudly
+    with pytest.raises(RuntimeError):
+        ms.rasterization_sh(*[a.detach() for a in A[:4]], torch.zeros(300, 3, 15, device=DEV), intr, extr, 64, 48, 0.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ms.rasterization_sh(*[a.detach().cpu() for a in A], intr, extr, 64, 48, 0.0)
