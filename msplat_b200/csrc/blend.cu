@@ -22,6 +22,8 @@
 //    (12 shuffles for 10 values instead of 50) and leave the SM as ONE red.global per value per
 //    warp, into a packed 32-byte gradient record; the reference issues (6+C) atomics per lane;
 //  * the backward walks only list positions below the tile's max ncontrib.
+#include <stdlib.h>
+
 #include "blend_math.cuh"
 
 namespace msb {
@@ -95,7 +97,7 @@ __device__ __forceinline__ void stage_issue(Stage<CH>& st, int slot, int id, con
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
+__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel_v1(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
@@ -249,7 +251,7 @@ __device__ __forceinline__ int red_slot(int lane) {
 }
 
 template <int CH>
-__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v1(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
@@ -404,8 +406,316 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
     cp_async_wait<0>();
 }
 
+
+// ================================================================================================
+// v2 kernels: branch-free pair math + deferred shared-memory gradient reduction
+// ================================================================================================
+// Forward.  Same traversal as v1; the per-pair body has no divergent branches: a pair that fails
+// a test blends with weight 0 (ffma(T, 0 * f, F) == F), so the image is bit-identical to v1 and
+// to the reference, and a warp-visit costs ~40 instead of ~64 issue slots.
+template <int CH>
+__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
+                                                          const float* __restrict__ featp, int fstride, int foff,
+                                                          const int* __restrict__ ids,
+                                                          const int2* __restrict__ tile_range, float bg,
+                                                          int c_valid, int W, int H, int write_aux,
+                                                          float* __restrict__ final_T, int* __restrict__ ncontrib,
+                                                          float* __restrict__ image) {
+    extern __shared__ __align__(16) unsigned char bl_raw[];
+    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
+    const int tile = blockIdx.y * gxt + blockIdx.x;
+    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const bool inside = px < W && py < H;
+    bool done = !inside;
+
+    const int2 range = tile_range[tile];
+    const int n = range.y - range.x;
+    const int nb = (n + BL_BATCH - 1) / BL_BATCH;
+
+    float T = 1.0f;
+    int last = 0;
+    float F[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) F[k] = 0.f;
+
+    int id_next = 0;
+    if (nb > 0) {
+        if (tid < n) stage_issue<CH>(stages[0], tid, ids[range.x + tid], rec, featp, fstride, foff);
+        cp_async_commit();
+        if (BL_BATCH + tid < n) id_next = ids[range.x + BL_BATCH + tid];
+    }
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<0>();
+        if (__syncthreads_and(done)) break;
+        if (b + 1 < nb) {
+            if ((b + 1) * BL_BATCH + tid < n)
+                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            cp_async_commit();
+            if ((b + 2) * BL_BATCH + tid < n) id_next = ids[range.x + (b + 2) * BL_BATCH + tid];
+        }
+        const Stage<CH>& st = stages[b & 1];
+        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
+        const int base1 = b * BL_BATCH + 1;
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            bool hit = false;
+            if (k0 + lane < cnt) {
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
+                                  (r0.y - r1.w > wy1);
+                hit = !miss;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 r0 = st.rec[2 * j];      // u, v, cx, cy   (broadcast LDS.128)
+                const float4 r1 = st.rec[2 * j + 1];  // cz, opacity, hx, hy
+                const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
+                const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
+                const float G = ex2_approx(fmul(power, kLog2e));
+                const float alpha = fmin_ftz(fmul(r1.y, G), kAlphaMax);
+                const bool ok = !done && !(power > 0.0f) && !(alpha < kAlphaMin);
+                const float nT = fmul(T, fadd(-alpha, 1.0f));
+                const bool term = ok && (nT < kTmin);  // alpha_blending.cu:90-94: entry not blended
+                const bool blend = ok && !term;
+                done = done || term;
+                const float a = blend ? alpha : 0.0f;
+                const float* f = &st.feat[j * CH];
+#pragma unroll
+                for (int k = 0; k < CH; k += 4) {
+                    const float4 fv = *reinterpret_cast<const float4*>(f + k);
+                    F[k] = ffma(T, fmul(a, fv.x), F[k]);
+                    F[k + 1] = ffma(T, fmul(a, fv.y), F[k + 1]);
+                    F[k + 2] = ffma(T, fmul(a, fv.z), F[k + 2]);
+                    F[k + 3] = ffma(T, fmul(a, fv.w), F[k + 3]);
+                }
+                T = blend ? nT : T;
+                last = blend ? base1 + j : last;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    cp_async_wait<0>();
+    if (inside) {
+        const long long pix = (long long)py * W + px;
+        if (write_aux) {
+            final_T[pix] = T;
+            ncontrib[pix] = last;
+        }
+        const long long hw = (long long)H * W;
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
+    }
+}
+
+// Backward.  Per warp-visit every lane produces NV = 6 + CH gradient contributions.  v1 reduced
+// them across the warp with a transposing butterfly (~68 issue slots per visit).  v2 parks them
+// in a per-warp shared-memory buffer [K visits][NV values][32 lanes] (row stride 36 floats:
+// conflict-free for the column writes and for the 16-byte row reads) and, every K visits, lane r
+// sums row r with 8 LDS.128 and issues one red.global: ~25 issue slots per visit.  The pair body
+// is branch-free: a failing pair runs with alpha = G = 0, which makes all of its contributions
+// exact zeros and leaves the replay state (T, suffix colour S) untouched.  The suffix colour is
+// carried as S_k = sum_{j>i} f_jk alpha_j T_j (identical algebra to the reference's accum_rec
+// recurrence, alpha_blending.cu:205-229: T_i (f - accum_rec) = f T_i - S / (1 - alpha_i)).
+template <int CH, int KV>
+struct BwdRed {
+    static constexpr int NV = 6 + CH;
+    static constexpr int K = KV;  // visits per flush, K * NV <= 32: CH=4 -> 3 (or 2), CH=8 -> 2, CH=16 -> 1
+    static constexpr int STRIDE = 36;
+    static constexpr int FLOATS = K * NV * STRIDE;  // per warp
+};
+
+template <int CH, int KV>
+__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+                                                          const float* __restrict__ featp, int fstride, int foff,
+                                                          const int* __restrict__ ids,
+                                                          const int2* __restrict__ tile_range, float bg,
+                                                          int c_valid, int W, int H,
+                                                          const float* __restrict__ final_T,
+                                                          const int* __restrict__ ncontrib,
+                                                          const float* __restrict__ dL_dimage,
+                                                          float* __restrict__ grec, float* __restrict__ gfeat,
+                                                          int geom_grads) {
+    using R = BwdRed<CH, KV>;
+    static_assert(R::K * R::NV <= 32 && R::K <= 4, "reduction rows must fit one warp");
+    constexpr int NV = R::NV;
+    extern __shared__ __align__(16) unsigned char bl_raw[];
+    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
+    float* s_red = reinterpret_cast<float*>(bl_raw + 2 * sizeof(Stage<CH>));
+    __shared__ int s_id[2][BL_BATCH];
+    __shared__ int s_max[BL_NT / 32];
+    __shared__ int s_bid[BL_NT / 32][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
+    const int tile = blockIdx.y * gxt + blockIdx.x;
+    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const bool inside = px < W && py < H;
+    const long long pix = (long long)py * W + px;
+    const long long hw = (long long)H * W;
+
+    const int2 range = tile_range[tile];
+    const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
+    int wmax = lc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    int maxc = 0;
+#pragma unroll
+    for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
+    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
+
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    float dpix[CH], S[CH];
+    float bgdot = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
+        S[k] = 0.f;
+        bgdot = fmaf(bg, dpix[k], bgdot);
+    }
+    const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
+
+    // this lane's role at flush time: row `lane` of the buffer = value (lane % NV) of visit (lane / NV)
+    const int my_k = lane / NV, my_v = lane - my_k * NV;
+    float* gptr = nullptr;
+    int gstride = 0;
+    if (lane < R::K * NV) {
+        if (my_v < 6) {
+            if (geom_grads) { gptr = grec + my_v; gstride = 8; }
+        } else if (my_v - 6 < c_valid) {
+            gptr = gfeat + foff + (my_v - 6);
+            gstride = fstride;
+        }
+    }
+    float* rb = s_red + warp * R::FLOATS;
+    int* bidw = s_bid[warp];
+    int nbuf = 0;
+
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < nbuf * NV) {
+            const float4* r = reinterpret_cast<const float4*>(rb + lane * R::STRIDE);
+            float4 a = r[0], c = r[1];
+#pragma unroll
+            for (int i = 2; i < 8; i += 2) {
+                const float4 x = r[i], y = r[i + 1];
+                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w;
+            }
+            const float sum = ((a.x + c.x) + (a.y + c.y)) + ((a.z + c.z) + (a.w + c.w));
+            if (gptr != nullptr && sum != 0.f) atomicAdd(gptr + (long long)bidw[my_k] * gstride, sum);
+        }
+        __syncwarp();
+        nbuf = 0;
+    };
+
+    // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
+    int id_next = 0;
+    if (nb > 0) {
+        if (tid < maxc) {
+            const int id = ids[range.x + maxc - 1 - tid];
+            s_id[0][tid] = id;
+            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
+        }
+        cp_async_commit();
+        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
+    }
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (b + 1 < nb) {
+            if ((b + 1) * BL_BATCH + tid < maxc) {
+                s_id[(b + 1) & 1][tid] = id_next;
+                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            }
+            cp_async_commit();
+            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
+        }
+        const Stage<CH>& st = stages[b & 1];
+        const int* sid = s_id[b & 1];
+        const int cnt = min(BL_BATCH, maxc - b * BL_BATCH);
+        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
+        if (pos0 - (cnt - 1) >= wmax) continue;    // whole batch lies beyond every pixel of this warp
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            bool hit = false;
+            if (k0 + lane < cnt) {
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
+                                  (r0.y - r1.w > wy1);
+                hit = !miss && (pos0 - (k0 + lane) < wmax);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 r0 = st.rec[2 * j];
+                const float4 r1 = st.rec[2 * j + 1];
+                const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
+                const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
+                const float Graw = ex2_approx(fmul(power, kLog2e));
+                const float araw = fmin_ftz(fmul(r1.y, Graw), kAlphaMax);
+                // alpha_blending.cu:185-187 (pos < lc) and :190-203 (power / alpha tests)
+                const bool valid = (pos0 - j < lc) && !(power > 0.0f) && !(araw < kAlphaMin);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                const float alpha = valid ? araw : 0.0f;
+                const float G = valid ? Graw : 0.0f;
+                const float rinv = rcp_approx(1.0f - alpha);  // == 1 for a failing pair
+                T = T * rinv;                                  // :205
+                const float wgt = alpha * T;
+                float* w = rb + nbuf * (NV * R::STRIDE) + lane;
+                float dL_dalpha = nbg * rinv;                  // :222-229
+                float f[CH];
+#pragma unroll
+                for (int k = 0; k < CH; k += 4) {
+                    const float4 fv = *reinterpret_cast<const float4*>(&st.feat[j * CH + k]);
+                    f[k] = fv.x; f[k + 1] = fv.y; f[k + 2] = fv.z; f[k + 3] = fv.w;
+                }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const float fk = f[k];
+                    dL_dalpha = fmaf(fmaf(fk, T, -S[k] * rinv), dpix[k], dL_dalpha);  // :213-217
+                    S[k] = fmaf(fk, wgt, S[k]);
+                    w[(6 + k) * R::STRIDE] = wgt * dpix[k];                            // :218-219
+                }
+                const float dL_dG = r1.y * dL_dalpha;  // :231
+                const float gdl = G * dL_dG;
+                w[0 * R::STRIDE] = gdl * (-dx * r0.z - dy * r0.w);  // :232-237
+                w[1 * R::STRIDE] = gdl * (-dy * r1.x - dx * r0.w);
+                w[2 * R::STRIDE] = -0.5f * gdl * dx * dx;            // :238-242
+                w[3 * R::STRIDE] = -gdl * dx * dy;
+                w[4 * R::STRIDE] = -0.5f * gdl * dy * dy;
+                w[5 * R::STRIDE] = G * dL_dalpha;                    // :243
+                if (lane == 0) bidw[nbuf] = sid[j];
+                if (++nbuf == R::K) flush();
+            }
+        }
+    }
+    if (nbuf > 0) flush();
+    cp_async_wait<0>();
+}
+
 static inline int pick_fwd_ch(int rem) { return rem >= 32 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4; }
 static inline int pick_bwd_ch(int rem) { return rem >= 16 ? 16 : rem > 4 ? 8 : 4; }
+
+// temporary A/B switch for profiling: MSB_BLEND_V1=1 selects the v1 kernels
+static bool blend_use_v1() {
+    static const int v = [] { const char* e = getenv("MSB_BLEND_V1"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v != 0;
+}
 
 template <int CH>
 static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
@@ -417,26 +727,56 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
                                              (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_fwd: cudaFuncSetAttribute failed");
     }
+    if (blend_use_v1()) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(blend_fwd_kernel_v1<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        blend_fwd_kernel_v1<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                           write_aux, final_T, ncontrib, image);
+        return check_launch("alpha_blending_fwd");
+    }
     blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
                                                     final_T, ncontrib, image);
     return check_launch("alpha_blending_fwd");
+}
+
+static int bwd_k_override() {
+    static const int v = [] { const char* e = getenv("MSB_BWD_K"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <int CH, int KV>
+static int launch_bwd_v2(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
+                         const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
+                         const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
+    const size_t smem = 2 * sizeof(Stage<CH>) + (size_t)(BL_NT / 32) * BwdRed<CH, KV>::FLOATS * sizeof(float);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    }
+    blend_bwd_kernel<CH, KV><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
+                                                        ncontrib, dL_dimage, grec, gfeat, geom);
+    return check_launch("alpha_blending_bwd");
 }
 
 template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
                       const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
-    const size_t smem = 2 * sizeof(Stage<CH>);
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    if (blend_use_v1()) {
+        const size_t smem1 = 2 * sizeof(Stage<CH>);
+        if (smem1 > 40 * 1024) cudaFuncSetAttribute(blend_bwd_kernel_v1<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        blend_bwd_kernel_v1<CH><<<grid, BL_NT, smem1, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                            final_T, ncontrib, dL_dimage, grec, gfeat, geom);
+        return check_launch("alpha_blending_bwd");
     }
-    blend_bwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
-                                                    ncontrib, dL_dimage, grec, gfeat, geom);
-    return check_launch("alpha_blending_bwd");
+    constexpr int KDEF = 32 / (6 + CH);
+    // CH = 4: K = 2 keeps the CTA at 48 KB of shared memory (4 CTAs/SM); K = 3 (59 KB, 3 CTAs/SM) measured 2.5 % slower
+    if (CH == 4 && bwd_k_override() != 3)
+        return launch_bwd_v2<CH, (CH == 4 ? 2 : KDEF)>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                      final_T, ncontrib, dL_dimage, grec, gfeat, geom);
+    return launch_bwd_v2<CH, KDEF>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib,
+                                   dL_dimage, grec, gfeat, geom);
 }
-
 
 // channel-chunk dispatcher of the forward pass (reference D1: alpha_blending.cu:248-394)
 static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,

@@ -32,6 +32,8 @@
 namespace msb {
 
 constexpr int RP_NT = 256;
+// SH rows (channels) fetched together per lane group: 4 x 16 B in flight per lane (2 when a lane already holds >8 floats per row)
+__host__ __device__ constexpr int rp_cu(int deg) { return sh_iters(deg) * (sh_vec(deg) ? 4 : 1) > 8 ? 2 : 4; }
 __host__ __device__ constexpr int rp_gpb(int deg) { return deg <= 4 ? 256 : deg <= 6 ? 128 : 64; }
 __host__ __device__ constexpr int rp_bs(int deg) { return (sh_dim(deg) * (rp_gpb(deg) + 1) + 3) / 4 * 4; }
 
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(RP_NT) render_pre_fwd_kernel(
     constexpr int UNITS = sh_units(DEG);
     constexpr int WD = VEC ? 4 : 1;
     constexpr int GROUPS = RP_NT / LPR;
+    constexpr int CU = rp_cu(DEG);
     extern __shared__ __align__(16) float sm[];
     float* s_xyz = sm;             // [G,3]   -> reused as the rec slab [G,8] after phase 1
     float* s_scale = sm + 3 * G;   // [G,3]
@@ -176,29 +179,40 @@ __global__ void __launch_bounds__(RP_NT) render_pre_fwd_kernel(
             for (int j = 0; j < WD; ++j) b[it * WD + j] = (act && un < UNITS) ? s_B[(un * WD + j) * GS + gl] : 0.f;
         }
         const long long row0 = (g0 + gl) * Cs;
-        for (int ch = 0; ch < Cs; ++ch) {
-            const float* rp = shs + (row0 + ch) * D;
-            float acc = 0.f;
+        // rows are fetched CU channels at a time so that every lane keeps CU * IT 16-byte loads
+        // in flight (a load -> fma -> shuffle chain per channel is latency-bound)
+        for (int c0 = 0; c0 < Cs; c0 += CU) {
+            float xv[CU][IT * WD];
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int un = s + it * LPR;
-                if (VEC) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (act && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
-                    acc = fmaf(x.x, b[it * WD + 0], acc);
-                    acc = fmaf(x.y, b[it * WD + (WD > 1 ? 1 : 0)], acc);
-                    acc = fmaf(x.z, b[it * WD + (WD > 2 ? 2 : 0)], acc);
-                    acc = fmaf(x.w, b[it * WD + (WD > 3 ? 3 : 0)], acc);
-                } else {
-                    const float x = (act && un < UNITS) ? __ldg(rp + un) : 0.f;
-                    acc = fmaf(x, b[it * WD], acc);
+            for (int cc = 0; cc < CU; ++cc) {
+                const bool chv = act && (c0 + cc < Cs);
+                const float* rp = shs + (row0 + c0 + cc) * D;
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const int un = s + it * LPR;
+                    if (VEC) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (chv && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
+                        xv[cc][it * WD + 0] = x.x;
+                        xv[cc][it * WD + (WD > 1 ? 1 : 0)] = x.y;
+                        xv[cc][it * WD + (WD > 2 ? 2 : 0)] = x.z;
+                        xv[cc][it * WD + (WD > 3 ? 3 : 0)] = x.w;
+                    } else {
+                        xv[cc][it * WD] = (chv && un < UNITS) ? __ldg(rp + un) : 0.f;
+                    }
                 }
             }
-            acc = group_sum<LPR>(acc);
-            if (act && s == 0) {
-                float val = acc + sh_bias;
-                if (clamp) val = fmaxf(val, 0.f);
-                s_feat[(size_t)gl * Cpad + ch] = val;
+#pragma unroll
+            for (int cc = 0; cc < CU; ++cc) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < IT * WD; ++i) acc = fmaf(xv[cc][i], b[i], acc);
+                acc = group_sum<LPR>(acc);
+                if (act && s == 0 && c0 + cc < Cs) {
+                    float val = acc + sh_bias;
+                    if (clamp) val = fmaxf(val, 0.f);
+                    s_feat[(size_t)gl * Cpad + c0 + cc] = val;
+                }
             }
         }
     }
@@ -229,6 +243,7 @@ __global__ void __launch_bounds__(RP_NT) render_pre_bwd_kernel(
     constexpr int UNITS = sh_units(DEG);
     constexpr int WD = VEC ? 4 : 1;
     constexpr int GROUPS = RP_NT / LPR;
+    constexpr int CU = rp_cu(DEG);
     extern __shared__ __align__(16) float sm[];
     float* s_xyz = sm;             // [G,3]  -> dL_dxyz slab
     float* s_scale = sm + 3 * G;   // [G,3]  -> dL_dscale slab
@@ -299,63 +314,69 @@ __global__ void __launch_bounds__(RP_NT) render_pre_bwd_kernel(
             }
         }
         const long long row0 = (g0 + gl) * Cs;
-        for (int ch = 0; ch < Cs; ++ch) {
-            const float* rp = shs + (row0 + ch) * D;
-            float* op = dL_dshs + (row0 + ch) * D;
-            const float gv = lv ? s_gfeat[(size_t)gl * Cpad + ch] : 0.f;
-            float sv[IT * WD];
-            float acc = 0.f;
+        for (int c0 = 0; c0 < Cs; c0 += CU) {
+            // fetch CU coefficient rows at once (memory-level parallelism), then consume them
+            float sv[CU][IT * WD];
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int un = s + it * LPR;
-                if (VEC) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lv && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
-                    sv[it * WD + 0] = x.x;
-                    sv[it * WD + (WD > 1 ? 1 : 0)] = x.y;
-                    sv[it * WD + (WD > 2 ? 2 : 0)] = x.z;
-                    sv[it * WD + (WD > 3 ? 3 : 0)] = x.w;
-                    acc = fmaf(x.x, b[it * WD + 0], acc);
-                    acc = fmaf(x.y, b[it * WD + (WD > 1 ? 1 : 0)], acc);
-                    acc = fmaf(x.z, b[it * WD + (WD > 2 ? 2 : 0)], acc);
-                    acc = fmaf(x.w, b[it * WD + (WD > 3 ? 3 : 0)], acc);
-                } else {
-                    const float x = (lv && un < UNITS) ? __ldg(rp + un) : 0.f;
-                    sv[it * WD] = x;
-                    acc = fmaf(x, b[it * WD], acc);
+            for (int cc = 0; cc < CU; ++cc) {
+                const bool chv = lv && (c0 + cc < Cs);
+                const float* rp = shs + (row0 + c0 + cc) * D;
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const int un = s + it * LPR;
+                    if (VEC) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (chv && un < UNITS) x = ldg_stream4(reinterpret_cast<const float4*>(rp) + un);
+                        sv[cc][it * WD + 0] = x.x;
+                        sv[cc][it * WD + (WD > 1 ? 1 : 0)] = x.y;
+                        sv[cc][it * WD + (WD > 2 ? 2 : 0)] = x.z;
+                        sv[cc][it * WD + (WD > 3 ? 3 : 0)] = x.w;
+                    } else {
+                        sv[cc][it * WD] = (chv && un < UNITS) ? __ldg(rp + un) : 0.f;
+                    }
                 }
             }
-            // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
-            acc = group_sum<LPR>(acc);
-            const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gv;
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int un = s + it * LPR;
-                if (!(act && un < UNITS)) continue;
-                if (VEC) {
-                    float4 o = make_float4(b[it * WD] * dv, b[it * WD + (WD > 1 ? 1 : 0)] * dv,
-                                           b[it * WD + (WD > 2 ? 2 : 0)] * dv, b[it * WD + (WD > 3 ? 3 : 0)] * dv);
-                    float4* q = reinterpret_cast<float4*>(op) + un;
-                    if (accumulate) {
-                        if (dv != 0.f) {
-                            const float4 old = *q;
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            for (int cc = 0; cc < CU; ++cc) {
+                const int ch = c0 + cc;
+                if (ch >= Cs) break;  // uniform across the block
+                float* op = dL_dshs + (row0 + ch) * D;
+                const float gv = lv ? s_gfeat[(size_t)gl * Cpad + ch] : 0.f;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < IT * WD; ++i) acc = fmaf(sv[cc][i], b[i], acc);
+                // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
+                acc = group_sum<LPR>(acc);
+                const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gv;
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const int un = s + it * LPR;
+                    if (!(act && un < UNITS)) continue;
+                    if (VEC) {
+                        float4 o = make_float4(b[it * WD] * dv, b[it * WD + (WD > 1 ? 1 : 0)] * dv,
+                                               b[it * WD + (WD > 2 ? 2 : 0)] * dv, b[it * WD + (WD > 3 ? 3 : 0)] * dv);
+                        float4* q = reinterpret_cast<float4*>(op) + un;
+                        if (accumulate) {
+                            if (dv != 0.f) {
+                                const float4 old = *q;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                *q = o;
+                            }
+                        } else {
                             *q = o;
                         }
                     } else {
-                        *q = o;
-                    }
-                } else {
-                    const float o = b[it * WD] * dv;
-                    if (accumulate) {
-                        if (dv != 0.f) op[un] += o;
-                    } else {
-                        op[un] = o;
+                        const float o = b[it * WD] * dv;
+                        if (accumulate) {
+                            if (dv != 0.f) op[un] += o;
+                        } else {
+                            op[un] = o;
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < IT * WD; ++i) wacc[i] = fmaf(sv[i], dv, wacc[i]);
+                for (int i = 0; i < IT * WD; ++i) wacc[i] = fmaf(sv[cc][i], dv, wacc[i]);
+            }
         }
         if (lv) {
 #pragma unroll
