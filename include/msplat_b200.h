@@ -85,18 +85,22 @@ int msb_compute_sh_bwd(const float* shs, const float* dirs, const uint8_t* visib
  * replaces torch.cumsum + computeGaussianKey + torch.sort + torch.gather +
  * computeTileGaussianRange (msplat/sort_gaussian.py:42-52, src/sort_gaussian.cu:74-142).
  * Two phases because M = sum(tiles) sizes the output:
- *   1. msb_sort_scan: offsets[P] = inclusive int32 cumsum of tiles; the int64 total is copied
- *      asynchronously to *total_host (PINNED host memory) -- synchronise `stream` before reading;
- *   2. msb_sort_gaussian: key duplication, onesweep radix sort over 32 + ceil(log2 T) bits,
- *      tile ranges.  idx_sorted [M] int32, tile_range [T,2] int32 (empty tiles (0,0)). */
+ *   1. msb_sort_scan: the int64 total M is copied asynchronously to *total_host (PINNED host
+ *      memory) -- synchronise `stream` before reading; offsets [P] (may be NULL) receives the
+ *      inclusive int32 cumsum of tiles (torch.cumsum equivalent, not needed by phase 2);
+ *   2. msb_sort_gaussian: stable LSD radix sort of the 64-bit key (tile << 32 | depth bits) over
+ *      the duplication slots -- the 4 depth-digit onesweep passes run on the P Gaussians before
+ *      duplication, the ceil(bits(T-1)/8) tile-digit passes on the M duplicates -- then tile
+ *      ranges.  idx_sorted [M] int32, tile_range [T,2] int32 (empty tiles (0,0)); bit-exact with
+ *      the reference.  msb_sort_num_passes = 4 + tile-digit passes. */
 size_t msb_sort_scan_workspace_bytes(int P);
 int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* total_host, void* ws,
                   size_t ws_bytes, void* stream);
 int msb_sort_num_passes(int W, int H);
-size_t msb_sort_workspace_bytes(long long M, int W, int H);
-int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles,
-                      const int32_t* offsets, int P, long long M, int W, int H, int32_t* idx_sorted,
-                      int32_t* tile_range, void* ws, size_t ws_bytes, int sm_count, void* stream);
+size_t msb_sort_workspace_bytes(int P, long long M, int W, int H);
+int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int P,
+                      long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws,
+                      size_t ws_bytes, int sm_count, void* stream);
 
 /* ---- alpha_blending -----------------------------------------------------------------------
  * replaces alphaBlendingForward / alphaBlendingBackward (src/alpha_blending.cu:248-573)

@@ -45,8 +45,8 @@ def _declare(lib):
         "msb_sort_scan_workspace_bytes": (SZ, [I]),
         "msb_sort_scan": (I, [P, I, P, P, P, SZ, V]),
         "msb_sort_num_passes": (I, [I, I]),
-        "msb_sort_workspace_bytes": (SZ, [LL, I, I]),
-        "msb_sort_gaussian": (I, [P, P, P, P, P, I, LL, I, I, P, P, P, SZ, I, V]),
+        "msb_sort_workspace_bytes": (SZ, [I, LL, I, I]),
+        "msb_sort_gaussian": (I, [P, P, P, P, I, LL, I, I, P, P, P, SZ, I, V]),
         "msb_blend_cpad": (I, [I]),
         "msb_blend_fwd_workspace_bytes": (SZ, [I, I]),
         "msb_blend_bwd_workspace_bytes": (SZ, [I, I]),

@@ -11,22 +11,36 @@
 // Defined-behaviour choices where the reference is UB: depth bits are masked to 32 bits and a
 // Gaussian never writes more than tiles[idx] entries.
 //
+// The order the reference produces is the stable LSD radix order of the 64-bit key over the
+// duplication slots.  All duplicates of a Gaussian share the low key word (its depth bits), so
+// the four depth-digit passes commute with the duplication: they are run on the P Gaussians
+// (8 B per element) instead of on the M = sum(tiles) duplicates (12 B per element), and only
+// the tile-digit passes (ceil(bits(T-1)/8): 2 at 1080p and 4K) touch the duplicates, with a
+// 32-bit key (the tile id).  Stability of every pass keeps ties (same tile, same depth bits) in
+// Gaussian-index order, exactly like the stable sort of the slots.  Never-written slots are
+// all (key 0, idx 0) and therefore form a prefix of tile 0: they are emitted first.
+//
 // Pipeline (all integer work, HBM-bound):
-//   phase 1  scan      : 3 small kernels -> inclusive offsets[P], M (copied to pinned host memory)
-//   phase 2a duplicate : warp-cooperative key/value emission; the digit histograms of ALL radix
-//                        passes are accumulated on the fly (depth digits once per Gaussian), so
-//                        the keys are never re-read for a histogram pass            12 B/key
-//   phase 2b onesweep  : p = ceil((32 + bits(T-1)) / 8) passes of 8 bits; each pass is ONE kernel:
-//                        warp-ballot (match.any) ranking into shared-memory histograms, chained
-//                        scan with decoupled look-back on a (value|flag) word per digit, keys
-//                        exchanged through shared memory so global writes are coalesced  24 B/key/pass
-//   phase 2c ranges    : boundary detection on the sorted keys                          8 B/key
+//   phase 1  count     : M = sum(max(tiles,0)) -> pinned host memory (sizes the output)
+//   phase 2a keygen    : per Gaussian: emitted-entry count n, depth key (0xFFFFFFFF if n == 0),
+//                        digit histograms of the 4 depth passes, phantom-slot count Z
+//   phase 2b onesweep  : 4 passes of 8 bits over (depth key, Gaussian id), P elements; each pass is
+//                        ONE kernel: warp-ballot (match.any) ranking into shared-memory histograms,
+//                        chained scan with decoupled look-back on a (value|flag) word per digit,
+//                        keys exchanged through shared memory so global writes are coalesced
+//   phase 2c offsets   : exclusive scan of n in depth order (+Z)
+//   phase 2d duplicate : warp-cooperative emission of (tile id, Gaussian id) in depth order; the
+//                        histograms of the tile passes are accumulated on the fly
+//   phase 2e onesweep  : ceil(bits(T-1)/8) passes over (tile id, Gaussian id), M elements
+//   phase 2f ranges    : boundary detection on the sorted tile ids
+// Algorithmic bytes: 24 B/Gaussian keygen + 4 * 16 B/Gaussian + 24 B/Gaussian offsets/duplicate reads
+//                    + 8 B/key duplicate write + pt * 16 B/key + 4 B/key ranges.
 #include "geom.cuh"
 
 namespace msb {
 
 // ------------------------------------------------------------------------------------------------
-// phase 1: inclusive scan of tiles[P]
+// scans
 // ------------------------------------------------------------------------------------------------
 constexpr int SC_NT = 256;
 constexpr int SC_IPT = 8;
@@ -62,7 +76,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp /*[NTH/32 + 1]
     return res;
 }
 
-__global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int* __restrict__ tiles,
+// value i of the scanned sequence: max(vals[i], 0), or vals[perm[i]] when a permutation is given
+__device__ __forceinline__ int scan_value(const int* __restrict__ vals, const int* __restrict__ perm, long long i) {
+    return perm != nullptr ? vals[perm[i]] : max(vals[i], 0);
+}
+
+__global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int* __restrict__ vals,
+                                                                const int* __restrict__ perm,
                                                                 long long* __restrict__ bsum) {
     __shared__ long long s_part[SC_NT / 32];
     const long long base = (long long)blockIdx.x * SC_TILE;
@@ -70,7 +90,7 @@ __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k * SC_NT + threadIdx.x;
-        if (i < P) acc += max(tiles[i], 0);
+        if (i < P) acc += scan_value(vals, perm, i);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -83,7 +103,7 @@ __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int
     }
 }
 
-// single block: exclusive scan of bsum[nb] in place; total -> *total_dev (saturated to INT_MAX+)
+// single block: exclusive scan of bsum[nb] in place; total -> *total_dev
 __global__ void __launch_bounds__(1024) scan_spine_kernel(int nb, long long* __restrict__ bsum,
                                                           long long* __restrict__ total_dev) {
     __shared__ long long s_w[33];
@@ -119,9 +139,13 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(int nb, long long* __r
     if (threadIdx.x == 0) *total_dev = carry;
 }
 
-__global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __restrict__ tiles,
+// out[i] = (EXCL ? exclusive : inclusive) prefix of the sequence, plus *bias (if given)
+template <bool EXCL>
+__global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __restrict__ vals,
+                                                           const int* __restrict__ perm,
                                                            const long long* __restrict__ bsum,
-                                                           int* __restrict__ offsets) {
+                                                           const unsigned int* __restrict__ bias,
+                                                           int* __restrict__ out) {
     __shared__ int s_warp[SC_NT / 32 + 1];
     const long long base = (long long)blockIdx.x * SC_TILE + (long long)threadIdx.x * SC_IPT;
     int v[SC_IPT];
@@ -129,67 +153,124 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k;
-        v[k] = i < P ? max(tiles[i], 0) : 0;
+        v[k] = i < P ? scan_value(vals, perm, i) : 0;
         sum += v[k];
     }
     int total;
-    int run = block_excl_scan<SC_NT>(sum, s_warp, total) + (int)bsum[blockIdx.x];
+    int run = block_excl_scan<SC_NT>(sum, s_warp, total) + (int)bsum[blockIdx.x] + (bias ? (int)*bias : 0);
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
-        run += v[k];
         const long long i = base + k;
-        if (i < P) offsets[i] = run;  // inclusive, like torch.cumsum
+        if (EXCL) {
+            if (i < P) out[i] = run;
+            run += v[k];
+        } else {
+            run += v[k];
+            if (i < P) out[i] = run;  // inclusive, like torch.cumsum
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2a: key/value duplication + histograms of every radix pass
+// phase 2a: per-Gaussian depth key, emitted-entry count, depth-digit histograms
 // ------------------------------------------------------------------------------------------------
-constexpr int MAX_PASS = 8;
+constexpr int KG_NT = 256;
+constexpr int MAX_TPASS = 4;  // tile id < 2^31
+
+__global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, const float2* __restrict__ uv,
+                                                       const float* __restrict__ depth,
+                                                       const int* __restrict__ radius,
+                                                       const int* __restrict__ tiles, int gx, int gy,
+                                                       unsigned int* __restrict__ dkeys, int* __restrict__ dvals,
+                                                       int* __restrict__ cnt,
+                                                       unsigned int* __restrict__ hist /*[4][256]*/,
+                                                       unsigned int* __restrict__ zcount) {
+    __shared__ unsigned int s_hist[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += KG_NT) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    unsigned int zsum = 0;
+    const long long nchunks = ((long long)P + KG_NT - 1) / KG_NT;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const long long i = chunk * KG_NT + threadIdx.x;
+        int n = 0;
+        unsigned int key = 0xffffffffu;
+        if (i < P) {
+            const int slots = max(tiles[i], 0);
+            const int rad = radius[i];
+            if (rad > 0 && slots > 0) {  // sort_gaussian.cu:26
+                const float2 c = uv[i];
+                const Rect q = get_rect(c.x, c.y, rad, gx, gy);
+                n = min(max((q.x1 - q.x0) * (q.y1 - q.y0), 0), slots);
+            }
+            zsum += (unsigned)(slots - n);  // never-written slots stay (0, 0): sort_gaussian.cu:98-99
+            if (n > 0) key = __float_as_uint(depth[i]);
+            dkeys[i] = key;
+            dvals[i] = (int)i;
+            cnt[i] = n;
+        }
+        // histograms: non-emitting Gaussians all carry digit 255 -> one aggregated add per warp
+        const unsigned ne = __ballot_sync(0xffffffffu, i < P && n == 0);
+        if (n > 0) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 255u)], 1u);
+        }
+        if (lane == 0 && ne) {
+            const unsigned c = __popc(ne);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + 255], c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+    if (lane == 0 && zsum) atomicAdd(zcount, zsum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += KG_NT) {
+        const unsigned int c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 2d: duplication in depth order + histograms of the tile-digit passes
+// ------------------------------------------------------------------------------------------------
 constexpr int DUP_NT = 256;
 constexpr int DUP_SMALL = 8;
 
-__global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const float2* __restrict__ uv,
-                                                           const float* __restrict__ depth,
-                                                           const int* __restrict__ radius,
-                                                           const int* __restrict__ tiles,
-                                                           const int* __restrict__ offsets, int gx, int gy,
-                                                           int npass, unsigned long long* __restrict__ keys,
-                                                           int* __restrict__ vals,
+__global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const int* __restrict__ order /*[P] depth order*/,
+                                                           const int* __restrict__ cnt,
+                                                           const int* __restrict__ start_sorted,
+                                                           const float2* __restrict__ uv,
+                                                           const int* __restrict__ radius, int gx, int gy,
+                                                           int npass, const unsigned int* __restrict__ zcount,
+                                                           unsigned int* __restrict__ keys, int* __restrict__ vals,
                                                            unsigned int* __restrict__ hist /*[npass][256]*/) {
-    __shared__ unsigned int s_hist[MAX_PASS * 256];
+    __shared__ unsigned int s_hist[MAX_TPASS * 256];
     for (int i = threadIdx.x; i < npass * 256; i += DUP_NT) s_hist[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    // phantom prefix: Z entries (tile 0, idx 0)
+    const unsigned int Z = *zcount;
+    for (long long e = (long long)blockIdx.x * DUP_NT + threadIdx.x; e < Z; e += (long long)gridDim.x * DUP_NT) {
+        keys[e] = 0u;
+        vals[e] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && Z)
+        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256], Z);
     const long long nchunks = ((long long)P + DUP_NT - 1) / DUP_NT;
     for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const long long i = chunk * DUP_NT + threadIdx.x;
-        int n = 0, z = 0, start = 0, x0 = 0, y0 = 0, w = 1;
-        unsigned int dbits = 0;
+        int n = 0, start = 0, x0 = 0, y0 = 0, w = 1, id = 0;
         if (i < P) {
-            const int slots = max(tiles[i], 0);
-            start = offsets[i] - slots;  // == cumsum[i-1] (sort_gaussian.cu:32)
-            const int rad = radius[i];
-            if (rad > 0) {  // sort_gaussian.cu:26
-                const float2 c = uv[i];
-                const Rect q = get_rect(c.x, c.y, rad, gx, gy);
+            id = order[i];
+            n = cnt[id];
+            if (n > 0) {
+                start = start_sorted[i];
+                const float2 c = uv[id];
+                const Rect q = get_rect(c.x, c.y, radius[id], gx, gy);
                 x0 = q.x0;
                 y0 = q.y0;
                 w = max(q.x1 - q.x0, 1);
-                n = min(max((q.x1 - q.x0) * (q.y1 - q.y0), 0), slots);
-                dbits = __float_as_uint(depth[i]);
-            }
-            z = slots - n;
-            if (n > 0) {
-                for (int p = 0; p < 4 && p < npass; ++p)
-                    atomicAdd(&s_hist[p * 256 + ((dbits >> (8 * p)) & 255u)], (unsigned)n);
-            }
-            if (z > 0) {
-                for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256], (unsigned)z);
-                for (int e = 0; e < z; ++e) {  // never-written slots stay (0, 0): sort_gaussian.cu:98-99
-                    keys[start + n + e] = 0ull;
-                    vals[start + n + e] = 0;
-                }
             }
         }
         // small footprints: each lane emits its own run
@@ -197,9 +278,9 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const float2* 
             int tx = x0, ty = y0;
             for (int e = 0; e < n; ++e) {
                 const unsigned int tile = (unsigned)(ty * gx + tx);
-                keys[start + e] = ((unsigned long long)tile << 32) | dbits;
-                vals[start + e] = (int)i;
-                for (int p = 4; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & 255u)], 1u);
+                keys[start + e] = tile;
+                vals[start + e] = id;
+                for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & 255u)], 1u);
                 if (++tx == x0 + w) {
                     tx = x0;
                     ++ty;
@@ -217,14 +298,13 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const float2* 
             const int bx0 = __shfl_sync(0xffffffffu, x0, src);
             const int by0 = __shfl_sync(0xffffffffu, y0, src);
             const int bw = __shfl_sync(0xffffffffu, w, src);
-            const unsigned bd = __shfl_sync(0xffffffffu, dbits, src);
-            const int bi = (int)(chunk * DUP_NT + (threadIdx.x & ~31) + src);
+            const int bid = __shfl_sync(0xffffffffu, id, src);
             for (int e = lane; e < bn; e += 32) {
                 const int ry = e / bw, rx = e - ry * bw;
                 const unsigned int tile = (unsigned)((by0 + ry) * gx + bx0 + rx);
-                keys[bstart + e] = ((unsigned long long)tile << 32) | bd;
-                vals[bstart + e] = bi;
-                for (int p = 4; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * (p - 4))) & 255u)], 1u);
+                keys[bstart + e] = tile;
+                vals[bstart + e] = bid;
+                for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & 255u)], 1u);
             }
         }
     }
@@ -236,7 +316,7 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const float2* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2b: one onesweep pass (8-bit digit) over (key64, val32) pairs
+// one onesweep pass (8-bit digit) over (key32, val32) pairs
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_NT = 256;
 constexpr int RS_WARPS = RS_NT / 32;
@@ -245,13 +325,13 @@ constexpr int RS_TILE = RS_NT * RS_IPT;  // 4096 keys per CTA
 constexpr unsigned int RS_FLAG_AGG = 1u << 30;
 constexpr unsigned int RS_FLAG_PRE = 2u << 30;
 constexpr unsigned int RS_VALUE_MASK = (1u << 30) - 1u;
+constexpr int RS_LB = 8;  // look-back window per round trip
 
 struct RsSmem {
-    unsigned long long keys[RS_TILE];    // 32 KB exchange buffer
+    unsigned int keys[RS_TILE];          // 16 KB exchange buffer
     int vals[RS_TILE];                   // 16 KB
     unsigned int whist[RS_WARPS][256];   //  8 KB per-warp digit counts -> per-warp offsets
-    unsigned int bin_start[256];         // tile-local exclusive digit offsets
-    long long gadj[256];                 // global base of the digit minus bin_start
+    int gadj[256];                       // global base of the digit minus its tile-local start
     int scan_tmp[RS_NT / 32 + 1];
     int tile_id;
 };
@@ -265,17 +345,15 @@ __device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(RS_NT) onesweep_kernel(int M, int pass, const unsigned long long* __restrict__ kin,
-                                                         const int* __restrict__ vin,
-                                                         unsigned long long* __restrict__ kout,
-                                                         int* __restrict__ vout,
-                                                         const unsigned int* __restrict__ hist /*[256] this pass*/,
-                                                         unsigned int* __restrict__ status /*[ntiles][256]*/,
-                                                         unsigned int* __restrict__ ticket) {
+__global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, const unsigned int* __restrict__ kin,
+                                                            const int* __restrict__ vin,
+                                                            unsigned int* __restrict__ kout, int* __restrict__ vout,
+                                                            const unsigned int* __restrict__ hist /*[256] this pass*/,
+                                                            unsigned int* __restrict__ status /*[ntiles][256]*/,
+                                                            unsigned int* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
     RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int shift = 8 * pass;
 
     if (tid == 0) sm.tile_id = (int)atomicAdd(ticket, 1u);  // tiles are ordered by start time
 #pragma unroll
@@ -283,40 +361,54 @@ __global__ void __launch_bounds__(RS_NT) onesweep_kernel(int M, int pass, const 
     __syncthreads();
     const int tile = sm.tile_id;
     const long long tile_base = (long long)tile * RS_TILE;
-    const int valid = (int)min((long long)RS_TILE, (long long)M - tile_base);
+    const int valid = (int)min((long long)RS_TILE, (long long)N - tile_base);
 
     // ---- load (warp-striped: element order = warp, item, lane) --------------------------------
-    unsigned long long key[RS_IPT];
-    int val[RS_IPT];
+    unsigned int key[RS_IPT];
     unsigned short rank[RS_IPT];
     const int wbase = warp * (32 * RS_IPT);
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
         const int e = wbase + i * 32 + lane;
-        if (e < valid) {
-            key[i] = kin[tile_base + e];
-            val[i] = vin[tile_base + e];
-        } else {
-            key[i] = ~0ull;  // sorts after everything; digit 255 in every pass
-            val[i] = 0;
-        }
+        key[i] = e < valid ? kin[tile_base + e] : 0xffffffffu;  // padding sorts last: digit 255 in every pass
     }
 
     // ---- rank inside the warp with match.any (warp-ballot ranking) ------------------------------
+    // All 16 match.any are issued first (independent, pipelined); the only serial chain left is one
+    // shared-memory atomic per round on the warp's private digit counters.
     const unsigned lt_mask = (1u << lane) - 1u;
+    // The peer mask (lanes holding the same digit) is built from 8 ballots, one per digit bit:
+    // match.any.sync costs time proportional to the number of DISTINCT values in the warp (measured:
+    // a pass over uniformly distributed digits ran 1.7x slower than one over 4 distinct digits).
+    unsigned peers[RS_IPT];
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        unsigned base = 0;
-        if (lane == leader) {
-            base = sm.whist[warp][d];
-            sm.whist[warp][d] = base + __popc(peers);
+        const unsigned d = key[i] >> shift;
+        unsigned m = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
         }
+        peers[i] = m;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        const unsigned d = (key[i] >> shift) & 255u;
+        const int leader = __ffs(peers[i]) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&sm.whist[warp][d], (unsigned)__popc(peers[i]));
+        __syncwarp();  // orders the counters between rounds (stability of the rank)
         base = __shfl_sync(0xffffffffu, base, leader);
-        rank[i] = (unsigned short)(base + __popc(peers & lt_mask));
-        __syncwarp();
+        rank[i] = (unsigned short)(base + __popc(peers[i] & lt_mask));
+    }
+    // payload: fetched now (the match masks are dead), lands while the digit offsets are resolved
+    int val[RS_IPT];
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        const int e = wbase + i * 32 + lane;
+        val[i] = e < valid ? vin[tile_base + e] : 0;
     }
     __syncthreads();
 
@@ -330,31 +422,43 @@ __global__ void __launch_bounds__(RS_NT) onesweep_kernel(int M, int pass, const 
     }
     if (tid == 255) count -= (unsigned)(RS_TILE - valid);  // padding keys are not real
     unsigned int* my_status = status + (size_t)tile * 256 + tid;
-    st_relaxed(my_status, (tile == 0 ? RS_FLAG_PRE : RS_FLAG_AGG) | count);
+    if (tile != 0) st_relaxed(my_status, RS_FLAG_AGG | count);  // as early as possible: successors sum it
 
-    // exclusive scan over digits of the global histogram and of the tile histogram
+    // tile-local exclusive digit offsets; tile 0 also scans the global histogram and folds the
+    // global digit base into the prefix it publishes, so every other tile receives it through
+    // the look-back and needs no scan of its own
     int tot;
-    const unsigned int gbase = (unsigned)block_excl_scan<RS_NT>((int)hist[tid], sm.scan_tmp, tot);
     const unsigned int lbase = (unsigned)block_excl_scan<RS_NT>((int)count, sm.scan_tmp, tot);
-
     unsigned int excl = 0;
-    if (tile > 0) {
+    if (tile == 0) {
+        excl = (unsigned)block_excl_scan<RS_NT>((int)hist[tid], sm.scan_tmp, tot);
+        st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
+    } else {
+        // decoupled look-back, RS_LB predecessors per round trip (independent loads in flight);
+        // a serial walk costs one L2 latency per predecessor and dominated the pass
         int j = tile - 1;
         while (true) {
-            const unsigned int* p = status + (size_t)j * 256 + tid;
-            unsigned int v = ld_relaxed(p);
-            while ((v & ~RS_VALUE_MASK) == 0u) {
-                __nanosleep(20);
-                v = ld_relaxed(p);
+            unsigned int v[RS_LB];
+#pragma unroll
+            for (int k = 0; k < RS_LB; ++k)
+                v[k] = (j - k >= 0) ? ld_relaxed(status + (size_t)(j - k) * 256 + tid) : RS_FLAG_PRE;
+            int used = 0;
+            bool done = false;
+#pragma unroll
+            for (int k = 0; k < RS_LB; ++k) {
+                if (!done && used == k && (v[k] & ~RS_VALUE_MASK) != 0u) {
+                    excl += v[k] & RS_VALUE_MASK;
+                    used = k + 1;
+                    done = (v[k] & RS_FLAG_PRE) != 0u;
+                }
             }
-            excl += v & RS_VALUE_MASK;
-            if (v & RS_FLAG_PRE) break;
-            --j;
+            if (done) break;
+            j -= used;
+            if (used == 0) __nanosleep(20);
         }
         st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
     }
-    sm.bin_start[tid] = lbase;
-    sm.gadj[tid] = (long long)gbase + (long long)excl - (long long)lbase;
+    sm.gadj[tid] = (int)excl - (int)lbase;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) sm.whist[w][tid] += lbase;  // warp offset inside the tile
     __syncthreads();
@@ -362,7 +466,7 @@ __global__ void __launch_bounds__(RS_NT) onesweep_kernel(int M, int pass, const 
     // ---- exchange through shared memory (tile-local sorted order) ------------------------------
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+        const unsigned d = (key[i] >> shift) & 255u;
         const unsigned pos = sm.whist[warp][d] + rank[i];
         sm.keys[pos] = key[i];
         sm.vals[pos] = val[i];
@@ -372,27 +476,27 @@ __global__ void __launch_bounds__(RS_NT) onesweep_kernel(int M, int pass, const 
     // ---- coalesced scatter ----------------------------------------------------------------------
 #pragma unroll 4
     for (int j = tid; j < valid; j += RS_NT) {
-        const unsigned long long k = sm.keys[j];
-        const unsigned d = (unsigned)(k >> shift) & 255u;
-        const long long g = sm.gadj[d] + j;
+        const unsigned int k = sm.keys[j];
+        const unsigned d = (k >> shift) & 255u;
+        const long long g = (long long)sm.gadj[d] + j;
         kout[g] = k;
         vout[g] = sm.vals[j];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2c: tile ranges from the sorted keys (sort_gaussian.cu:45-71); tile_range pre-zeroed
+// phase 2f: tile ranges from the sorted tile ids (sort_gaussian.cu:45-71); tile_range pre-zeroed
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tile_range_kernel(int M, const unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(256) tile_range_kernel(int M, const unsigned int* __restrict__ keys,
                                                          int2* __restrict__ tile_range, int T) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
-    const unsigned int cur = (unsigned int)(keys[i] >> 32);
+    const unsigned int cur = keys[i];
     if (cur >= (unsigned)T) return;  // cannot happen for keys produced by duplicate_kernel
     if (i == 0) tile_range[cur].x = 0;
     if (i == M - 1) tile_range[cur].y = M;
     if (i == 0) return;
-    const unsigned int prev = (unsigned int)(keys[i - 1] >> 32);
+    const unsigned int prev = keys[i - 1];
     if (prev != cur) {
         if (prev < (unsigned)T) tile_range[prev].y = (int)i;
         tile_range[cur].x = (int)i;
@@ -401,29 +505,44 @@ __global__ void __launch_bounds__(256) tile_range_kernel(int M, const unsigned l
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int num_passes(int T) {
+// digit passes over the tile id
+static int tile_passes(int T) {
     int bits = 0;
     while (bits < 31 && (1ll << bits) < (long long)T) ++bits;  // bits needed for tile ids 0..T-1
-    return (32 + bits + 7) / 8;
+    return (bits + 7) / 8;
 }
 
 struct SortLayout {
-    size_t keys_a, keys_b, vals_tmp, hist, ticket, status, total;
-    int npass, ntiles_rs;
+    size_t dkeys[2], dvals[2], cnt, start, tkeys[2], tvals, bsum, zero0, hist, ticket, zcount, status_d, status_t, total;
+    int tpass, ntiles_d, ntiles_t, nb_scan;
 };
 
-static SortLayout sort_layout(long long M, int T) {
+static SortLayout sort_layout(int P, long long M, int T) {
     SortLayout L;
-    L.npass = num_passes(T);
-    L.ntiles_rs = (int)((M + RS_TILE - 1) / RS_TILE);
+    L.tpass = tile_passes(T);
+    L.ntiles_d = (int)(((long long)P + RS_TILE - 1) / RS_TILE);
+    L.ntiles_t = (int)((M + RS_TILE - 1) / RS_TILE);
+    L.nb_scan = (int)(((long long)P + SC_TILE - 1) / SC_TILE);
     size_t off = 0;
-    L.keys_a = off; off = align_up(off + (size_t)M * 8, 256);
-    L.keys_b = off; off = align_up(off + (size_t)M * 8, 256);
-    L.vals_tmp = off; off = align_up(off + (size_t)M * 4, 256);
-    // zero-initialised region: hist | ticket | status
-    L.hist = off; off = align_up(off + (size_t)MAX_PASS * 256 * 4, 256);
-    L.ticket = off; off = align_up(off + (size_t)MAX_PASS * 4, 256);
-    L.status = off; off = align_up(off + (size_t)L.npass * (size_t)L.ntiles_rs * 256 * 4, 256);
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    for (int k = 0; k < 2; ++k) L.dkeys[k] = take((size_t)P * 4);
+    for (int k = 0; k < 2; ++k) L.dvals[k] = take((size_t)P * 4);
+    L.cnt = take((size_t)P * 4);
+    L.start = take((size_t)P * 4);
+    for (int k = 0; k < 2; ++k) L.tkeys[k] = take((size_t)M * 4);
+    L.tvals = take((size_t)M * 4);
+    L.bsum = take((size_t)(L.nb_scan + 2) * 8);
+    // zero-initialised region: hist | ticket | zcount | status
+    L.zero0 = off;
+    L.hist = take((size_t)(4 + MAX_TPASS) * 256 * 4);
+    L.ticket = take((size_t)(4 + MAX_TPASS) * 4);
+    L.zcount = take(4);
+    L.status_d = take((size_t)4 * L.ntiles_d * 256 * 4);
+    L.status_t = take((size_t)L.tpass * L.ntiles_t * 256 * 4);
     L.total = off;
     return L;
 }
@@ -440,9 +559,10 @@ size_t msb_sort_scan_workspace_bytes(int P) {
     return (nb + 2) * sizeof(long long);
 }
 
-// Phase 1.  offsets[P] = inclusive int32 cumsum of max(tiles, 0); the 64-bit total is copied
-// asynchronously into *total_host (pinned host memory): the caller synchronises the stream
-// before reading it.
+// Phase 1.  The 64-bit total M = sum(max(tiles, 0)) is copied asynchronously into *total_host
+// (pinned host memory): the caller synchronises the stream before reading it.  If offsets is not
+// NULL it also receives the inclusive int32 cumsum (torch.cumsum equivalent; the sort itself no
+// longer needs it).
 int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* total_host, void* ws, size_t ws_bytes,
                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -451,14 +571,14 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
         *total_host = 0;
         return MSB_OK;
     }
-    if (!tiles || !offsets || !ws) return set_error(MSB_ERR_ARG, "sort_scan: null pointer");
+    if (!tiles || !ws) return set_error(MSB_ERR_ARG, "sort_scan: null pointer");
     if (ws_bytes < msb_sort_scan_workspace_bytes(P)) return set_error(MSB_ERR_WORKSPACE, "sort_scan: workspace too small");
     const int nb = (P + SC_TILE - 1) / SC_TILE;
     long long* bsum = reinterpret_cast<long long*>(ws);
     long long* total_dev = bsum + nb;
-    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
+    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, nullptr, bsum);
     scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
-    scan_apply_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, bsum, offsets);
+    if (offsets) scan_apply_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, nullptr, bsum, nullptr, offsets);
     int rc = check_launch("sort_scan");
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
@@ -466,21 +586,23 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
     return MSB_OK;
 }
 
+// Number of 8-bit digit passes over the 64-bit key: 4 depth passes (on the Gaussians) plus the
+// tile-id passes (on the duplicates).
 int msb_sort_num_passes(int W, int H) {
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
-    return num_passes(gx * gy);
+    return 4 + tile_passes(gx * gy);
 }
 
-size_t msb_sort_workspace_bytes(long long M, int W, int H) {
+size_t msb_sort_workspace_bytes(int P, long long M, int W, int H) {
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
-    if (M <= 0) return 256;
-    return sort_layout(M, gx * gy).total;
+    if (M <= 0 || P <= 0) return 256;
+    return sort_layout(P, M, gx * gy).total;
 }
 
 // Phase 2.  idx_sorted[M] (int32) and tile_range[T, 2] (int32) are outputs owned by the caller.
-int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles,
-                      const int32_t* offsets, int P, long long M, int W, int H, int32_t* idx_sorted,
-                      int32_t* tile_range, void* ws, size_t ws_bytes, int sm_count, void* stream) {
+int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int P,
+                      long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws, size_t ws_bytes,
+                      int sm_count, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
     const int T = gx * gy;
@@ -489,43 +611,67 @@ int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     cudaError_t e = cudaMemsetAsync(tile_range, 0, (size_t)T * 2 * sizeof(int32_t), st);
     if (e != cudaSuccess) return set_error((int)e, "sort_gaussian: memset tile_range failed");
     if (M == 0 || P == 0) return MSB_OK;
-    if (!uv || !depth || !radius || !tiles || !offsets || !idx_sorted || !ws)
+    if (!uv || !depth || !radius || !tiles || !idx_sorted || !ws)
         return set_error(MSB_ERR_ARG, "sort_gaussian: null pointer");
-    const SortLayout L = sort_layout(M, T);
+    const SortLayout L = sort_layout(P, M, T);
     if (ws_bytes < L.total) return set_error(MSB_ERR_WORKSPACE, "sort_gaussian: workspace too small");
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
-    unsigned long long* kbuf[2] = {reinterpret_cast<unsigned long long*>(base + L.keys_a),
-                                   reinterpret_cast<unsigned long long*>(base + L.keys_b)};
-    int* vtmp = reinterpret_cast<int*>(base + L.vals_tmp);
-    // values ping-pong so that the last pass lands in idx_sorted
-    int* vbuf[2];
-    vbuf[L.npass % 2] = idx_sorted;
-    vbuf[(L.npass + 1) % 2] = vtmp;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(base + L.hist);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(base + L.ticket);
-    unsigned int* status = reinterpret_cast<unsigned int*>(base + L.status);
-    e = cudaMemsetAsync(base + L.hist, 0, L.total - L.hist, st);
+    auto U32 = [&](size_t o) { return reinterpret_cast<unsigned int*>(base + o); };
+    auto I32 = [&](size_t o) { return reinterpret_cast<int*>(base + o); };
+    unsigned int* hist = U32(L.hist);
+    unsigned int* ticket = U32(L.ticket);
+    unsigned int* zcount = U32(L.zcount);
+    e = cudaMemsetAsync(base + L.zero0, 0, L.total - L.zero0, st);
     if (e != cudaSuccess) return set_error((int)e, "sort_gaussian: memset workspace failed");
-
-    const long long nchunks = ((long long)P + DUP_NT - 1) / DUP_NT;
     const int sms = sm_count > 0 ? sm_count : 148;
-    const unsigned dup_grid = (unsigned)min(nchunks, (long long)sms * 8);
-    duplicate_kernel<<<dup_grid, DUP_NT, 0, st>>>(P, reinterpret_cast<const float2*>(uv), depth, radius, tiles, offsets,
-                                                  gx, gy, L.npass, kbuf[0], vbuf[0], hist);
-    int rc = check_launch("sort_gaussian/duplicate");
+    const long long nchunks = ((long long)P + KG_NT - 1) / KG_NT;
+    const unsigned sgrid = (unsigned)min(nchunks, (long long)sms * 8);
+
+    // 2a: depth keys
+    keygen_kernel<<<sgrid, KG_NT, 0, st>>>(P, reinterpret_cast<const float2*>(uv), depth, radius, tiles, gx, gy,
+                                           U32(L.dkeys[0]), I32(L.dvals[0]), I32(L.cnt), hist, zcount);
+    int rc = check_launch("sort_gaussian/keygen");
     if (rc) return rc;
 
-    static_assert(sizeof(RsSmem) <= 100 * 1024, "onesweep shared memory");
-    e = cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem));
-    if (e != cudaSuccess) return set_error((int)e, "sort_gaussian: cudaFuncSetAttribute failed");
-    for (int p = 0; p < L.npass; ++p) {
-        onesweep_kernel<<<L.ntiles_rs, RS_NT, sizeof(RsSmem), st>>>(
-            (int)M, p, kbuf[p % 2], vbuf[p % 2], kbuf[(p + 1) % 2], vbuf[(p + 1) % 2], hist + p * 256,
-            status + (size_t)p * L.ntiles_rs * 256, ticket + p);
-        rc = check_launch("sort_gaussian/onesweep");
+    static_assert(sizeof(RsSmem) <= 48 * 1024, "onesweep shared memory");
+    // 2b: four depth-digit passes over the Gaussians (ends in buffer 0)
+    for (int p = 0; p < 4; ++p) {
+        onesweep_kernel<<<L.ntiles_d, RS_NT, sizeof(RsSmem), st>>>(
+            P, 8 * p, U32(L.dkeys[p % 2]), I32(L.dvals[p % 2]), U32(L.dkeys[(p + 1) % 2]), I32(L.dvals[(p + 1) % 2]),
+            hist + p * 256, U32(L.status_d) + (size_t)p * L.ntiles_d * 256, ticket + p);
+        rc = check_launch("sort_gaussian/onesweep(depth)");
         if (rc) return rc;
     }
-    tile_range_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((int)M, kbuf[L.npass % 2],
+    const int* order = I32(L.dvals[0]);
+
+    // 2c: start offsets in depth order (exclusive scan of the emitted counts, + Z)
+    long long* bsum = reinterpret_cast<long long*>(base + L.bsum);
+    scan_block_sums_kernel<<<L.nb_scan, SC_NT, 0, st>>>(P, I32(L.cnt), order, bsum);
+    scan_spine_kernel<<<1, 1024, 0, st>>>(L.nb_scan, bsum, bsum + L.nb_scan);
+    scan_apply_kernel<true><<<L.nb_scan, SC_NT, 0, st>>>(P, I32(L.cnt), order, bsum, zcount, I32(L.start));
+    rc = check_launch("sort_gaussian/offsets");
+    if (rc) return rc;
+
+    // 2d: duplication; values ping-pong so that the last tile pass lands in idx_sorted
+    unsigned int* tk[2] = {U32(L.tkeys[0]), U32(L.tkeys[1])};
+    int* tv[2];
+    tv[L.tpass % 2] = idx_sorted;
+    tv[(L.tpass + 1) % 2] = I32(L.tvals);
+    unsigned int* thist = hist + 4 * 256;
+    duplicate_kernel<<<sgrid, DUP_NT, 0, st>>>(P, order, I32(L.cnt), I32(L.start), reinterpret_cast<const float2*>(uv),
+                                               radius, gx, gy, L.tpass, zcount, tk[0], tv[0], thist);
+    rc = check_launch("sort_gaussian/duplicate");
+    if (rc) return rc;
+
+    // 2e: tile-digit passes over the duplicates
+    for (int p = 0; p < L.tpass; ++p) {
+        onesweep_kernel<<<L.ntiles_t, RS_NT, sizeof(RsSmem), st>>>(
+            (int)M, 8 * p, tk[p % 2], tv[p % 2], tk[(p + 1) % 2], tv[(p + 1) % 2], thist + p * 256,
+            U32(L.status_t) + (size_t)p * L.ntiles_t * 256, ticket + 4 + p);
+        rc = check_launch("sort_gaussian/onesweep(tile)");
+        if (rc) return rc;
+    }
+    tile_range_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((int)M, tk[L.tpass % 2],
                                                                   reinterpret_cast<int2*>(tile_range), T);
     return check_launch("sort_gaussian/tile_range");
 }

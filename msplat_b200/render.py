@@ -92,30 +92,29 @@ class _RenderSHViews(torch.autograd.Function):
                 depth = torch.empty((P,), dtype=f32, device=dev)
                 radius = torch.empty((P,), dtype=i32, device=dev)
                 tiles = torch.empty((P,), dtype=i32, device=dev)
-                offsets = torch.empty((P,), dtype=i32, device=dev)
                 _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd, dev, ptr(x), ptr(s),
                           ptr(q), ptr(o), ptr(sh), ptr(I[b]), ptr(E[b]), P, Cs, D, int(with_depth), W, H, nearest,
                           extent, sh_bias, int(clamp), ptr(rec), ptr(featp), ptr(uv), ptr(depth), ptr(radius),
                           ptr(tiles))
                 ws1 = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
-                _lib.call("sort_scan", 3 if P else 0, L.msb_sort_scan, dev, ptr(tiles), P, ptr(offsets),
+                _lib.call("sort_scan", 2 if P else 0, L.msb_sort_scan, dev, ptr(tiles), P, None,
                           ptr(totals[b:]), ptr(ws1), ws1.numel())
-                views.append([rec, featp, uv, depth, radius, tiles, offsets])
+                views.append([rec, featp, uv, depth, radius, tiles])
             torch.cuda.current_stream(dev).synchronize()
             Ms = [int(totals[b]) for b in range(B)]
             # phase B: sort + blend per view
             saved = []
             for b in range(B):
-                rec, featp, uv, depth, radius, tiles, offsets = views[b]
+                rec, featp, uv, depth, radius, tiles = views[b]
                 M = Ms[b]
                 if M >= 2 ** 30:
                     raise RuntimeError(f"rasterization_sh: {M} tile intersections exceed the supported 2^30")
                 ids = torch.empty((M,), dtype=i32, device=dev)
                 tr = torch.empty((T, 2), dtype=i32, device=dev)
-                ws2 = torch.empty((L.msb_sort_workspace_bytes(M, W, H),), dtype=torch.uint8, device=dev)
-                nk = 2 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
+                ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, W, H),), dtype=torch.uint8, device=dev)
+                nk = 6 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
                 _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius), ptr(tiles),
-                          ptr(offsets), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
+                          P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
                 final_T = torch.empty((H, W), dtype=f32, device=dev)
                 ncontrib = torch.empty((H, W), dtype=i32, device=dev)
                 _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd, dev, ptr(rec), ptr(featp),

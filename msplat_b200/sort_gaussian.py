@@ -27,10 +27,9 @@ def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, til
         T = ((W + 15) // 16) * ((H + 15) // 16)
         tile_range = torch.empty((T, 2), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            offsets = torch.empty((P,), dtype=torch.int32, device=dev)
             ws1 = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
             total = _lib.pinned_i64(dev)
-            _lib.call("sort_scan", 3 if P else 0, L.msb_sort_scan, dev, ptr(t), P, ptr(offsets), ptr(total), ptr(ws1),
+            _lib.call("sort_scan", 2 if P else 0, L.msb_sort_scan, dev, ptr(t), P, None, ptr(total), ptr(ws1),
                       ws1.numel())
             # the one host<->device sync of the pipeline: M sizes the output (reference: two .item())
             torch.cuda.current_stream(dev).synchronize()
@@ -38,8 +37,8 @@ def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, til
             if M >= 2 ** 30:
                 raise RuntimeError(f"sort_gaussian: {M} tile intersections exceed the supported 2^30")
             idx_sorted = torch.empty((M,), dtype=torch.int32, device=dev)
-            ws2 = torch.empty((L.msb_sort_workspace_bytes(M, int(W), int(H)),), dtype=torch.uint8, device=dev)
-            nk = 2 + L.msb_sort_num_passes(int(W), int(H)) if (M > 0 and P > 0) else 0
-            _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(u), ptr(d), ptr(r), ptr(t), ptr(offsets), P,
+            ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, int(W), int(H)),), dtype=torch.uint8, device=dev)
+            nk = 6 + L.msb_sort_num_passes(int(W), int(H)) if (M > 0 and P > 0) else 0  # keygen, 3 scan, duplicate, ranges + passes
+            _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(u), ptr(d), ptr(r), ptr(t), P,
                       M, int(W), int(H), ptr(idx_sorted), ptr(tile_range), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
     return idx_sorted, tile_range

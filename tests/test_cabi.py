@@ -61,7 +61,7 @@ def test_argument_validation_without_gpu():
     assert L.msb_sort_num_passes(1920, 1080) == 6      # T = 8160 -> 13 tile bits -> 45 bits
     assert L.msb_sort_num_passes(3840, 2160) == 6      # T = 32400 -> 47 bits
     assert L.msb_sort_num_passes(256, 256) == 5        # T = 256 -> 40 bits
-    assert L.msb_sort_workspace_bytes(1000, 64, 64) > 1000 * 20
+    assert L.msb_sort_workspace_bytes(500, 1000, 64, 64) > 1000 * 12 + 500 * 24
     # negative P / null pointers are rejected before any launch
     rc = L.msb_project_point_fwd(None, None, None, 5, 64, 64, 0.0, 1.3, None, None, None)
     assert rc == -1 and b"project_point_fwd" in L.msb_last_error()
