@@ -220,7 +220,7 @@ def run_gpu(args, api, impl):
                 w_.wait()
         return loss.detach()
 
-    def measure(step):
+    def measure(step, stages=False):
         """-> (ms per step resident, renders/s resident, renders/s e2e, launches, timing)"""
         dev_in = (intr_h.to(dev), extr_h.to(dev), cent_h.to(dev), G)
         for _ in range(args.warmup):
@@ -228,7 +228,6 @@ def run_gpu(args, api, impl):
         barrier_sync(world)
         if ours:
             _lib.reset_launches()
-            _lib.TIMING = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
@@ -238,13 +237,28 @@ def run_gpu(args, api, impl):
         barrier_sync(world)
         t1 = time.time()
         launches = _lib.launches() if ours else 0
-        timing = _lib.TIMING if ours else None
-        if ours:
-            _lib.TIMING = None
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
+        timing = None
+        if ours and stages:
+            # per-C-ABI-call durations: same steps again, serialised on one stream (no sort/blend overlap),
+            # each call bracketed by CUDA events on its launching stream
+            from msplat_b200 import render as _render
+            prev, _render.OVERLAP = _render.OVERLAP, False
+            step(*dev_in)
+            barrier_sync(world)
+            _lib.TIMING = []
+            e0.record()
+            for _ in range(args.steps):
+                step(*dev_in)
+            e1.record()
+            barrier_sync(world)
+            timing, _lib.TIMING = _lib.TIMING, None
+            _render.OVERLAP = prev
+            serial_ms = e0.elapsed_time(e1) / args.steps
+            timing = (timing, serial_ms)
         # e2e: per step H2D of the step's inputs (cameras + cotangent) from pinned memory, D2H of the loss
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         barrier_sync(world)
@@ -267,7 +281,8 @@ def run_gpu(args, api, impl):
         from msplat_b200 import _lib
     fused = ours and args.api == "fused"
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
-    ms_per_step, value, e2e_value, launches, timing, (t_wall0, t_wall1) = measure(step_fused if fused else step_steps)
+    ms_per_step, value, e2e_value, launches, timing, (t_wall0, t_wall1) = measure(step_fused if fused else step_steps,
+                                                                                 stages=True)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     api_note = ("msplat_b200.rasterization_sh_views (fused view-batch Function)" if fused else
@@ -287,6 +302,8 @@ def run_gpu(args, api, impl):
     }
     if ours:
         out["gpu_launches"] = launches
+        timing, serial_ms = timing
+        out["serial_ms_per_step"] = serial_ms  # same step with the two-stream overlap switched off (stage timings)
         out.update(stage_report(timing, args, api, params, cams_host[0], G, clocks, V))
         if fused and not args.no_steps_api:
             s_ms, s_val, s_e2e, _, _, _ = measure(step_steps)

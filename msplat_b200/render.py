@@ -30,6 +30,25 @@ from ._lib import as_f32, ptr
 
 __all__ = ["rasterization_sh", "rasterization_sh_views"]
 
+# Two-stream schedule for view batches: the sort of view b+1 (latency-bound integer passes) runs on a
+# side stream under the forward blend of view b (issue-bound), and the fused preprocess backward of
+# view b (HBM-bound) under the backward blend of view b+1.  Results are unaffected (same kernels,
+# same accumulation order); set to False to serialise everything on the caller's stream (used by
+# bench.py for per-kernel timings).
+OVERLAP = True
+_side_streams = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    idx = torch.device(dev).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _side_streams:
+        # high priority: its CTAs are dispatched as soon as blend CTAs retire instead of queueing behind the
+        # thousands of tile CTAs of the blend kernel launched before them
+        _side_streams[idx] = torch.cuda.Stream(device=idx, priority=-1)
+    return _side_streams[idx]
+
 
 def rasterization_sh(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intr: Tensor, extr: Tensor,
@@ -100,10 +119,12 @@ class _RenderSHViews(torch.autograd.Function):
                 _lib.call("sort_scan", 2 if P else 0, L.msb_sort_scan, dev, ptr(tiles), P, None,
                           ptr(totals[b:]), ptr(ws1), ws1.numel())
                 views.append([rec, featp, uv, depth, radius, tiles])
-            torch.cuda.current_stream(dev).synchronize()
+            main = torch.cuda.current_stream(dev)
+            main.synchronize()
             Ms = [int(totals[b]) for b in range(B)]
-            # phase B: sort + blend per view
-            saved = []
+            side = _side_stream(dev) if (OVERLAP and B > 1) else None
+            # phase B: sort (side stream when overlapping) + blend (caller's stream) per view
+            saved, keep = [], []
             for b in range(B):
                 rec, featp, uv, depth, radius, tiles = views[b]
                 M = Ms[b]
@@ -112,15 +133,21 @@ class _RenderSHViews(torch.autograd.Function):
                 ids = torch.empty((M,), dtype=i32, device=dev)
                 tr = torch.empty((T, 2), dtype=i32, device=dev)
                 ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, W, H),), dtype=torch.uint8, device=dev)
-                nk = 6 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
-                _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius), ptr(tiles),
-                          P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
                 final_T = torch.empty((H, W), dtype=f32, device=dev)
                 ncontrib = torch.empty((H, W), dtype=i32, device=dev)
+                nk = 6 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
+                with torch.cuda.stream(side if side is not None else main):
+                    _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius),
+                              ptr(tiles), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
+                    if side is not None:
+                        main.wait_event(side.record_event())
                 _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd, dev, ptr(rec), ptr(featp),
                           ptr(ids), ptr(tr), bg, C, W, H, ptr(images[b]), ptr(final_T), ptr(ncontrib))
                 saved += [rec, featp, tiles, ids, tr, final_T, ncontrib]
+                keep += [uv, depth, radius, ws2]  # alive until both streams are joined (allocated on `main`)
                 views[b] = None
+            # all side-stream work is ordered before the last blend, hence before anything the caller enqueues next
+            del keep
         ctx.cfg = (B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth)
         ctx.cam_grad = (intrs.requires_grad, extrs.requires_grad)
         ctx.shapes = (tuple(opacity.shape), tuple(intrs.shape), tuple(extrs.shape))
@@ -148,17 +175,35 @@ class _RenderSHViews(torch.autograd.Function):
             for t in (dxyz, dscale, dquat, dop, dshs):
                 t.zero_()
         else:
-            grec = torch.empty((P, 8), dtype=f32, device=dev)
-            gfeat = torch.empty((P, cpad), dtype=f32, device=dev)
-            for b in range(B):
-                rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
-                _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
-                          ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
-                          ptr(grec), ptr(gfeat))
-                _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x), ptr(s), ptr(q),
-                          ptr(sh), ptr(I[b]), ptr(E[b]), ptr(tiles), ptr(grec), ptr(gfeat), P, Cs, D, int(with_depth),
-                          sh_bias, int(clamp), 1 if b > 0 else 0, ptr(dxyz), ptr(dscale), ptr(dquat), ptr(dop),
-                          ptr(dshs), ptr(dintr[b]) if need_i else None, ptr(dextr[b]) if need_e else None)
+            with torch.cuda.device(dev):
+                main = torch.cuda.current_stream(dev)
+                side = _side_stream(dev) if (OVERLAP and B > 1) else None
+                nbuf = 2 if side is not None else 1
+                grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(nbuf)]
+                gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(nbuf)]
+                done = [None] * B
+                if side is not None:
+                    side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
+                for b in range(B):
+                    rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
+                    k = b % nbuf
+                    if side is not None and b >= nbuf:
+                        main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
+                    _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
+                              ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
+                              ptr(grec[k]), ptr(gfeat[k]))
+                    with torch.cuda.stream(side if side is not None else main):
+                        if side is not None:
+                            side.wait_event(main.record_event())
+                        _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x), ptr(s),
+                                  ptr(q), ptr(sh), ptr(I[b]), ptr(E[b]), ptr(tiles), ptr(grec[k]), ptr(gfeat[k]), P, Cs,
+                                  D, int(with_depth), sh_bias, int(clamp), 1 if b > 0 else 0, ptr(dxyz), ptr(dscale),
+                                  ptr(dquat), ptr(dop), ptr(dshs), ptr(dintr[b]) if need_i else None,
+                                  ptr(dextr[b]) if need_e else None)
+                        if side is not None:
+                            done[b] = side.record_event()
+                if side is not None:
+                    main.wait_stream(side)
         op_shape = ctx.shapes[0]
         return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr, dextr, None, None, None, None, None, None,
                 None, None)
