@@ -65,20 +65,41 @@ def rasterization_sh(
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3,
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3,
 ) -> Tensor:
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
-    -> images [B,C,H,W]."""
+    -> images [B,C,H,W].
+
+    ``grad_sync`` (view-batch data parallelism): a ``torch.distributed`` process group
+    (or ``True`` for the default group).  The backward pass then returns the per-Gaussian gradients
+    already SUMMED over the ranks of that group: the Gaussians are processed in ``grad_chunks``
+    slabs, and the all-reduce of a finished slab (NCCL, its own stream) runs under the
+    preprocess-backward kernels of the following slabs instead of after the whole backward.
+    Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a
+    custom reducer: it is called with every finished gradient slab (in place) and may return an
+    object with ``.wait()``."""
     if intrs.dim() == 1:
         intrs = intrs[None].expand(extrs.shape[0], 4)
     return _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
-                                float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent))
+                                float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent),
+                                grad_sync, int(grad_chunks))
+
+
+def _resolve_group(grad_sync):
+    """-> process group to all-reduce over, or None when there is nothing to do."""
+    import torch.distributed as dist
+    if callable(grad_sync):
+        return grad_sync  # custom reducer: called as grad_sync(tensor_slab) -> None | object with .wait()
+    if grad_sync is None or grad_sync is False or not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = dist.group.WORLD if grad_sync is True else grad_sync
+    return group if dist.get_world_size(group) > 1 else None
 
 
 class _RenderSHViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scale, rotate, opacity, shs, intrs, extrs, W, H, bg, sh_bias, clamp, with_depth, nearest,
-                extent):
+                extent, grad_sync, grad_chunks):
         x, s, q = as_f32(xyz, "xyz"), as_f32(scale, "scale"), as_f32(rotate, "rotate")
         o, sh = as_f32(opacity, "opacity"), as_f32(shs, "shs")
         I, E = as_f32(intrs, "intrs"), as_f32(extrs, "extrs")
@@ -150,6 +171,7 @@ class _RenderSHViews(torch.autograd.Function):
             del keep
         ctx.cfg = (B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth)
         ctx.cam_grad = (intrs.requires_grad, extrs.requires_grad)
+        ctx.grad_sync = (grad_sync, grad_chunks)
         ctx.shapes = (tuple(opacity.shape), tuple(intrs.shape), tuple(extrs.shape))
         ctx.save_for_backward(x, s, q, sh, I, E, *saved)
         return images
@@ -175,38 +197,73 @@ class _RenderSHViews(torch.autograd.Function):
             for t in (dxyz, dscale, dquat, dop, dshs):
                 t.zero_()
         else:
+            group = _resolve_group(ctx.grad_sync[0])
+            outs = (dxyz, dscale, dquat, dop, dshs)
+
+            def pre_bwd(b, gr, gf, lo, hi):
+                """fused preprocess backward of view b for the Gaussians [lo, hi) (accumulates for b > 0)"""
+                _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x[lo:hi]),
+                          ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[b]), ptr(E[b]), ptr(saved[7 * b + 2][lo:hi]),
+                          ptr(gr[lo:hi]), ptr(gf[lo:hi]), hi - lo, Cs, D, int(with_depth), sh_bias, int(clamp),
+                          1 if b > 0 else 0, ptr(dxyz[lo:hi]), ptr(dscale[lo:hi]), ptr(dquat[lo:hi]), ptr(dop[lo:hi]),
+                          ptr(dshs[lo:hi]), ptr(dintr[b]) if need_i else None, ptr(dextr[b]) if need_e else None)
+
+            def blend_bwd(b, gr, gf):
+                rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
+                _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
+                          ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
+                          ptr(gr), ptr(gf))
+
             with torch.cuda.device(dev):
                 main = torch.cuda.current_stream(dev)
-                side = _side_stream(dev) if (OVERLAP and B > 1) else None
-                nbuf = 2 if side is not None else 1
-                grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(nbuf)]
-                gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(nbuf)]
-                done = [None] * B
-                if side is not None:
-                    side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
-                for b in range(B):
-                    rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
-                    k = b % nbuf
-                    if side is not None and b >= nbuf:
-                        main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
-                    _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
-                              ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
-                              ptr(grec[k]), ptr(gfeat[k]))
-                    with torch.cuda.stream(side if side is not None else main):
-                        if side is not None:
-                            side.wait_event(main.record_event())
-                        _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x), ptr(s),
-                                  ptr(q), ptr(sh), ptr(I[b]), ptr(E[b]), ptr(tiles), ptr(grec[k]), ptr(gfeat[k]), P, Cs,
-                                  D, int(with_depth), sh_bias, int(clamp), 1 if b > 0 else 0, ptr(dxyz), ptr(dscale),
-                                  ptr(dquat), ptr(dop), ptr(dshs), ptr(dintr[b]) if need_i else None,
-                                  ptr(dextr[b]) if need_e else None)
-                        if side is not None:
-                            done[b] = side.record_event()
-                if side is not None:
-                    main.wait_stream(side)
+                if group is not None:
+                    # data-parallel schedule: all blend backwards first (packed gradients kept per view), then
+                    # the preprocess backward slab by slab; a finished slab is all-reduced while the next runs
+                    import torch.distributed as dist
+                    grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(B)]
+                    gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(B)]
+                    for b in range(B):
+                        blend_bwd(b, grec[b], gfeat[b])
+                    nchunk = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
+                    step = ((P + nchunk - 1) // nchunk + 255) // 256 * 256  # slab starts stay 16-byte aligned
+                    works = []
+                    for lo in range(0, P, step):
+                        hi = min(P, lo + step)
+                        for b in range(B):
+                            pre_bwd(b, grec[b], gfeat[b], lo, hi)
+                        for t in outs:
+                            if callable(group):
+                                works.append(group(t[lo:hi]))
+                            else:
+                                works.append(dist.all_reduce(t[lo:hi], op=dist.ReduceOp.SUM, group=group,
+                                                             async_op=True))
+                    for w in works:
+                        if w is not None:
+                            w.wait()
+                else:
+                    side = _side_stream(dev) if (OVERLAP and B > 1) else None
+                    nbuf = 2 if side is not None else 1
+                    grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(nbuf)]
+                    gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(nbuf)]
+                    done = [None] * B
+                    if side is not None:
+                        side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
+                    for b in range(B):
+                        k = b % nbuf
+                        if side is not None and b >= nbuf:
+                            main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
+                        blend_bwd(b, grec[k], gfeat[k])
+                        with torch.cuda.stream(side if side is not None else main):
+                            if side is not None:
+                                side.wait_event(main.record_event())
+                            pre_bwd(b, grec[k], gfeat[k], 0, P)
+                            if side is not None:
+                                done[b] = side.record_event()
+                    if side is not None:
+                        main.wait_stream(side)
         op_shape = ctx.shapes[0]
         return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr, dextr, None, None, None, None, None, None,
-                None, None)
+                None, None, None, None)
 
 
 def _blend_passes_fwd(cpad: int, C: int) -> int:

@@ -138,6 +138,34 @@ def test_render_sh_views_equals_single_views(ms):
     grad_close(i4.grad, ia.grad.sum(0), rel=2e-3, eps=2e-4, what="shared dintr")
 
 
+def test_render_sh_grad_sync_slabs(ms):
+    """Data-parallel backward schedule: the reducer sees every gradient element exactly once, slab by
+    slab, and what it does to a slab is what the caller gets back (here: x2, i.e. two identical ranks)."""
+    P, W, H, bg, deg, Cs, nv = 5003, 200, 136, 0.0, 3, 3, 2
+    intr, extr = camera(W, H)
+    extrs = torch.stack([extr, extr.clone()]).to(DEV)
+    extrs[1, 0, 3] += 0.3
+    A = make_leaves(P, Cs, deg, 85, DEV)
+    B = make_leaves(P, Cs, deg, 85, DEV)
+    g = torch.randn(nv, Cs + 1, H, W, generator=torch.Generator().manual_seed(3)).to(DEV)
+    seen = []
+
+    def reducer(slab):
+        seen.append(tuple(slab.shape))
+        slab.mul_(2.0)
+
+    imgs = ms.rasterization_sh_views(*A, intr.to(DEV), extrs, W, H, bg, with_depth=True, grad_sync=reducer,
+                                     grad_chunks=3)
+    (imgs * g).sum().backward()
+    ref = ms.rasterization_sh_views(*B, intr.to(DEV), extrs, W, H, bg, with_depth=True)
+    assert torch.equal(imgs, ref)
+    (ref * g).sum().backward()
+    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B):
+        grad_close(a.grad, 2.0 * b.grad, rel=1e-3, eps=1e-4, what=f"slab-synced d{n}")
+    rows = sum(sh[0] for sh in seen if len(sh) == 3)  # the shs slabs
+    assert rows == P and len(seen) == 5 * 3
+
+
 def test_render_sh_vs_oracle(ms):
     P, W, H, bg, deg, Cs = 5000, 200, 120, 0.0, 3, 3
     intr, extr = camera(W, H)
