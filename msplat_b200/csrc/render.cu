@@ -83,7 +83,7 @@ __device__ __forceinline__ void slab_store_acc(float* __restrict__ g, const floa
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int DEG>
-__global__ void __launch_bounds__(RP_NT) render_pre_fwd_kernel(
+__global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel(
     int P, int Cs, int Cpad, int with_depth, const float* __restrict__ xyz, const float* __restrict__ scale,
     const float* __restrict__ quat, const float* __restrict__ opacity, const float* __restrict__ shs,
     const float* __restrict__ intr, const float* __restrict__ extr, int W, int H, float nearest, float extent,
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(RP_NT) render_pre_fwd_kernel(
 // backward
 // ------------------------------------------------------------------------------------------------
 template <int DEG, bool CAM>
-__global__ void __launch_bounds__(RP_NT) render_pre_bwd_kernel(
+__global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel(
     int P, int Cs, int Cpad, int with_depth, int accumulate, const float* __restrict__ xyz,
     const float* __restrict__ scale, const float* __restrict__ quat, const float* __restrict__ shs,
     const float* __restrict__ intr, const float* __restrict__ extr, float sh_bias, int clamp,
@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(RP_NT) render_pre_bwd_kernel(
     float* s_quat = sm + 6 * G;    // [G,4]  -> dL_dquat slab
     float* s_grec = sm + 10 * G;   // [G,8]
     float* s_B = sm + 18 * G;      // [D][GS]
-    float* s_W = s_B + rp_bs(DEG);  // [D][GS]
-    float* s_gfeat = s_W + rp_bs(DEG);                                            // [G,Cpad]
+    float* s_W = s_B;              // [D][GS]  aliases s_B: column gl is loaded into registers by the lane group
+                                   //          that owns Gaussian gl before the same group overwrites it with w
+    float* s_gfeat = s_B + rp_bs(DEG);                                            // [G,Cpad]
     unsigned* s_list = reinterpret_cast<unsigned*>(s_gfeat + (size_t)Cpad * G);   // [G]
     __shared__ int s_cnt;
     __shared__ float s_red[8 * 16];
@@ -457,7 +458,7 @@ static size_t rp_smem_fwd(int deg, int Cpad) {
 }
 static size_t rp_smem_bwd(int deg, int Cpad) {
     const int G = rp_gpb(deg);
-    return ((size_t)18 * G + 2 * (size_t)rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
+    return ((size_t)18 * G + (size_t)rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
 }
 
 struct RpFwdArgs {
