@@ -439,9 +439,9 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
 
     float T = 1.0f;
     int last = 0;
-    float F[CH];
+    f32x2 F2[CH / 2];  // accumulated colour, two channels per 64-bit register pair (FFMA2)
 #pragma unroll
-    for (int k = 0; k < CH; ++k) F[k] = 0.f;
+    for (int k = 0; k < CH / 2; ++k) F2[k] = pk2(0.f, 0.f);
 
     int id_next = 0;
     if (nb > 0) {
@@ -488,13 +488,12 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
                 done = done || term;
                 const float a = blend ? alpha : 0.0f;
                 const float* f = &st.feat[j * CH];
+                const f32x2 a2 = pk2(a, a), T2 = pk2(T, T);
 #pragma unroll
-                for (int k = 0; k < CH; k += 4) {
+                for (int k = 0; k < CH; k += 4) {  // F_k = fma(T, alpha * f_k, F_k), same rounding as the scalar ops
                     const float4 fv = *reinterpret_cast<const float4*>(f + k);
-                    F[k] = ffma(T, fmul(a, fv.x), F[k]);
-                    F[k + 1] = ffma(T, fmul(a, fv.y), F[k + 1]);
-                    F[k + 2] = ffma(T, fmul(a, fv.z), F[k + 2]);
-                    F[k + 3] = ffma(T, fmul(a, fv.w), F[k + 3]);
+                    F2[k / 2] = fma2(T2, mul2(a2, pk2(fv.x, fv.y)), F2[k / 2]);
+                    F2[k / 2 + 1] = fma2(T2, mul2(a2, pk2(fv.z, fv.w)), F2[k / 2 + 1]);
                 }
                 T = blend ? nT : T;
                 last = blend ? base1 + j : last;
@@ -511,8 +510,12 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
         }
         const long long hw = (long long)H * W;
 #pragma unroll
-        for (int k = 0; k < CH; ++k)
-            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
+        for (int k = 0; k < CH; k += 2) {
+            float f0, f1;
+            upk2(F2[k / 2], f0, f1);
+            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, f0);
+            if (k + 1 < c_valid) image[(k + 1) * hw + pix] = ffma(T, bg, f1);
+        }
     }
 }
 
@@ -578,13 +581,18 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
 
     const float T_final = inside ? final_T[pix] : 0.f;
     float T = T_final;
-    float dpix[CH], S[CH];
+    float dpix[CH];
+    f32x2 dpix2[CH / 2], S2[CH / 2];  // cotangent and suffix colour, two channels per 64-bit register pair
     float bgdot = 0.f;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
         dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
-        S[k] = 0.f;
         bgdot = fmaf(bg, dpix[k], bgdot);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k += 2) {
+        dpix2[k / 2] = pk2(dpix[k], dpix[k + 1]);
+        S2[k / 2] = pk2(0.f, 0.f);
     }
     const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
 
@@ -608,14 +616,17 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
         __syncwarp();
         if (lane < nbuf * NV) {
             const float4* r = reinterpret_cast<const float4*>(rb + lane * R::STRIDE);
-            float4 a = r[0], c = r[1];
+            const float4 r0 = r[0];
+            f32x2 a = pk2(r0.x, r0.y), c = pk2(r0.z, r0.w);
 #pragma unroll
-            for (int i = 2; i < 8; i += 2) {
-                const float4 x = r[i], y = r[i + 1];
-                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-                c.x += y.x; c.y += y.y; c.z += y.z; c.w += y.w;
+            for (int i = 1; i < 8; ++i) {
+                const float4 x = r[i];
+                a = add2(a, pk2(x.x, x.y));
+                c = add2(c, pk2(x.z, x.w));
             }
-            const float sum = ((a.x + c.x) + (a.y + c.y)) + ((a.z + c.z) + (a.w + c.w));
+            float slo, shi;
+            upk2(add2(a, c), slo, shi);
+            const float sum = slo + shi;
             if (gptr != nullptr && sum != 0.f) atomicAdd(gptr + (long long)bidw[my_k] * gstride, sum);
         }
         __syncwarp();
@@ -677,20 +688,31 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
                 T = T * rinv;                                  // :205
                 const float wgt = alpha * T;
                 float* w = rb + nbuf * (NV * R::STRIDE) + lane;
-                float dL_dalpha = nbg * rinv;                  // :222-229
-                float f[CH];
+                // channel math on packed pairs (FFMA2/FMUL2): per pair of channels
+                //   e = f T - S / (1 - alpha);  dL_dalpha += e . dpix;  S += f alpha T;  dL_dfeature = alpha T dpix
+                const f32x2 T2 = pk2(T, T), W2 = pk2(wgt, wgt), NR2 = pk2(-rinv, -rinv);
+                f32x2 dacc = pk2(nbg * rinv, 0.f);             // :222-229 (background term)
 #pragma unroll
                 for (int k = 0; k < CH; k += 4) {
                     const float4 fv = *reinterpret_cast<const float4*>(&st.feat[j * CH + k]);
-                    f[k] = fv.x; f[k + 1] = fv.y; f[k + 2] = fv.z; f[k + 3] = fv.w;
+                    const f32x2 fa = pk2(fv.x, fv.y), fb = pk2(fv.z, fv.w);
+                    const f32x2 ea = fma2(S2[k / 2], NR2, mul2(fa, T2));           // :213-217
+                    const f32x2 eb = fma2(S2[k / 2 + 1], NR2, mul2(fb, T2));
+                    dacc = fma2(ea, dpix2[k / 2], dacc);
+                    dacc = fma2(eb, dpix2[k / 2 + 1], dacc);
+                    S2[k / 2] = fma2(fa, W2, S2[k / 2]);
+                    S2[k / 2 + 1] = fma2(fb, W2, S2[k / 2 + 1]);
+                    float w0, w1, w2, w3;
+                    upk2(mul2(W2, dpix2[k / 2]), w0, w1);                          // :218-219
+                    upk2(mul2(W2, dpix2[k / 2 + 1]), w2, w3);
+                    w[(6 + k) * R::STRIDE] = w0;
+                    w[(7 + k) * R::STRIDE] = w1;
+                    w[(8 + k) * R::STRIDE] = w2;
+                    w[(9 + k) * R::STRIDE] = w3;
                 }
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const float fk = f[k];
-                    dL_dalpha = fmaf(fmaf(fk, T, -S[k] * rinv), dpix[k], dL_dalpha);  // :213-217
-                    S[k] = fmaf(fk, wgt, S[k]);
-                    w[(6 + k) * R::STRIDE] = wgt * dpix[k];                            // :218-219
-                }
+                float dlo, dhi;
+                upk2(dacc, dlo, dhi);
+                const float dL_dalpha = dlo + dhi;
                 const float dL_dG = r1.y * dL_dalpha;  // :231
                 const float gdl = G * dL_dG;
                 w[0 * R::STRIDE] = gdl * (-dx * r0.z - dy * r0.w);  // :232-237

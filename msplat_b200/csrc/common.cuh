@@ -84,6 +84,33 @@ MSB_HD float fmin_ftz(float a, float b) { return fminf(a, b); }
 MSB_HD int imin(int a, int b) { return a < b ? a : b; }
 MSB_HD int imax(int a, int b) { return a > b ? a : b; }
 
+// ---- packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2, one issue slot for two lanes of math) -----
+// Round-to-nearest, FTZ: bit-identical to the scalar __fmaf_rn / __fmul_rn / __fadd_rn results.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ---- streaming global access ------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
     float4 v;
