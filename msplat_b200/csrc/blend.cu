@@ -96,323 +96,9 @@ __device__ __forceinline__ void stage_issue(Stage<CH>& st, int slot, int id, con
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel_v1(const float4* __restrict__ rec,
-                                                          const float* __restrict__ featp, int fstride, int foff,
-                                                          const int* __restrict__ ids,
-                                                          const int2* __restrict__ tile_range, float bg,
-                                                          int c_valid, int W, int H, int write_aux,
-                                                          float* __restrict__ final_T, int* __restrict__ ncontrib,
-                                                          float* __restrict__ image) {
-    extern __shared__ __align__(16) unsigned char bl_raw[];
-    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
-    const int tile = blockIdx.y * gxt + blockIdx.x;
-    // warp -> 8x4 pixel block of the 16x16 tile
-    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const bool inside = px < W && py < H;
-    bool done = !inside;
-
-    const int2 range = tile_range[tile];
-    const int n = range.y - range.x;
-    const int nb = (n + BL_BATCH - 1) / BL_BATCH;
-
-    float T = 1.0f;
-    int last = 0;
-    float F[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) F[k] = 0.f;
-
-    // prologue: stage batch 0, prefetch the id of batch 1
-    int id_next = 0;
-    if (nb > 0) {
-        if (tid < n) stage_issue<CH>(stages[0], tid, ids[range.x + tid], rec, featp, fstride, foff);
-        cp_async_commit();
-        if (BL_BATCH + tid < n) id_next = ids[range.x + BL_BATCH + tid];
-    }
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait<0>();
-        // barrier: batch b is visible to everyone, everyone is done with batch b-1; also the vote
-        if (__syncthreads_and(done)) break;
-        if (b + 1 < nb) {
-            if ((b + 1) * BL_BATCH + tid < n)
-                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
-            cp_async_commit();
-            if ((b + 2) * BL_BATCH + tid < n) id_next = ids[range.x + (b + 2) * BL_BATCH + tid];
-        }
-        const Stage<CH>& st = stages[b & 1];
-        const int cnt = min(BL_BATCH, n - b * BL_BATCH);
-        const int base = b * BL_BATCH;
-        if (__all_sync(0xffffffffu, done)) continue;  // this warp's 32 pixels are finished
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-            // lane-parallel footprint test of 32 staged Gaussians against this warp's 8x4 block
-            bool hit = false;
-            if (k0 + lane < cnt) {
-                const float4 r0 = st.rec[2 * (k0 + lane)];
-                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
-                                  (r0.y - r1.w > wy1);
-                hit = !miss;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = k0 + __ffs(m) - 1;
-                m &= m - 1;
-                const float4 r0 = st.rec[2 * j];      // u, v, cx, cy   (broadcast LDS.128)
-                const float4 r1 = st.rec[2 * j + 1];  // cz, opacity, hx, hy
-                if (!done) {
-                    const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
-                    const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
-                    float G, alpha;
-                    if (pair_alpha(power, r1.y, G, alpha)) {
-                        const float nT = fmul(T, fadd(-alpha, 1.0f));
-                        if (nT < kTmin) {
-                            done = true;  // alpha_blending.cu:90-94: entry not blended
-                        } else {
-                            const float* f = &st.feat[j * CH];
-#pragma unroll
-                            for (int k = 0; k < CH; k += 4) {
-                                const float4 fv = *reinterpret_cast<const float4*>(f + k);
-                                F[k] = ffma(T, fmul(alpha, fv.x), F[k]);
-                                F[k + 1] = ffma(T, fmul(alpha, fv.y), F[k + 1]);
-                                F[k + 2] = ffma(T, fmul(alpha, fv.z), F[k + 2]);
-                                F[k + 3] = ffma(T, fmul(alpha, fv.w), F[k + 3]);
-                            }
-                            T = nT;
-                            last = base + j + 1;
-                        }
-                    }
-                }
-            }
-            if (__all_sync(0xffffffffu, done)) break;
-        }
-    }
-    cp_async_wait<0>();
-    if (inside) {
-        const long long pix = (long long)py * W + px;
-        if (write_aux) {
-            final_T[pix] = T;
-            ncontrib[pix] = last;
-        }
-        const long long hw = (long long)H * W;
-#pragma unroll
-        for (int k = 0; k < CH; ++k)
-            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward
-// ------------------------------------------------------------------------------------------------
-// Transposing butterfly: N per-lane values -> after 5 steps lane L holds, in v[0], the warp-wide
-// sum of ONE of the N values (which one: red_slot()).  ceil(N/2)+ceil(N/4)+... shuffles.
-template <int N, int OFF>
-struct WarpRed {
-    static __device__ __forceinline__ void run(float* v, bool const* upper) {
-        constexpr int Hn = (N + 1) / 2;
-        const bool up = upper[0];
-#pragma unroll
-        for (int i = 0; i < Hn; ++i) {
-            const float a = v[i];
-            const float b = (i + Hn < N) ? v[i + Hn] : 0.f;
-            const float send = up ? a : b;
-            const float keep = up ? b : a;
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-        }
-        WarpRed<Hn, OFF / 2>::run(v, upper + 1);
-    }
-};
-template <int N>
-struct WarpRed<N, 0> {
-    static __device__ __forceinline__ void run(float*, bool const*) {}
-};
-
-// which of the N values ends up in lane `lane` (or -1 if that lane holds nothing)
-template <int N>
-__device__ __forceinline__ int red_slot(int lane) {
-    int n[6];
-    n[0] = N;
-    for (int s = 0; s < 5; ++s) n[s + 1] = (n[s] + 1) / 2;
-    int p = 0;
-    bool ok = true;
-    for (int s = 4; s >= 0; --s) {  // unwind from the last step (offset 1) to the first (offset 16)
-        const int off = 16 >> s;
-        const int Hn = n[s + 1];
-        if (lane & off) {
-            if (p + Hn >= n[s]) ok = false;
-            p += Hn;
-        }
-    }
-    return ok ? p : -1;
-}
-
-template <int CH>
-__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v1(const float4* __restrict__ rec,
-                                                          const float* __restrict__ featp, int fstride, int foff,
-                                                          const int* __restrict__ ids,
-                                                          const int2* __restrict__ tile_range, float bg,
-                                                          int c_valid, int W, int H,
-                                                          const float* __restrict__ final_T,
-                                                          const int* __restrict__ ncontrib,
-                                                          const float* __restrict__ dL_dimage,
-                                                          float* __restrict__ grec, float* __restrict__ gfeat,
-                                                          int geom_grads) {
-    constexpr int NV = 6 + CH;
-    extern __shared__ __align__(16) unsigned char bl_raw[];
-    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
-    __shared__ int s_id[2][BL_BATCH];
-    __shared__ int s_max[BL_NT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
-    const int tile = blockIdx.y * gxt + blockIdx.x;
-    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const bool inside = px < W && py < H;
-    const long long pix = (long long)py * W + px;
-    const long long hw = (long long)H * W;
-
-    const int2 range = tile_range[tile];
-    const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
-    // tile-wide max -> only list positions [0, maxc) are ever needed
-    int wmax = lc;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int maxc = 0;
-#pragma unroll
-    for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
-    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
-
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    float dpix[CH], accum[CH], lastf[CH];
-    float bgdot = 0.f;
-#pragma unroll
-    for (int k = 0; k < CH; ++k) {
-        dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
-        accum[k] = 0.f;
-        lastf[k] = 0.f;
-        bgdot = fmaf(bg, dpix[k], bgdot);
-    }
-    float last_alpha = 0.f;
-
-    // this lane's role after the transposing reduction
-    const int slot = red_slot<NV>(lane);
-    bool upper[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s) upper[s] = (lane & (16 >> s)) != 0;
-    float* gptr = nullptr;   // base of this lane's gradient component
-    int gstride = 0;
-    if (slot >= 0 && slot < 6) {
-        if (geom_grads) { gptr = grec + slot; gstride = 8; }
-    } else if (slot >= 6 && slot - 6 < c_valid) {
-        gptr = gfeat + foff + (slot - 6);
-        gstride = fstride;
-    }
-
-    // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
-    int id_next = 0;
-    if (nb > 0) {
-        if (tid < maxc) {
-            const int id = ids[range.x + maxc - 1 - tid];
-            s_id[0][tid] = id;
-            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
-        }
-        cp_async_commit();
-        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
-    }
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (b + 1 < nb) {
-            if ((b + 1) * BL_BATCH + tid < maxc) {
-                s_id[(b + 1) & 1][tid] = id_next;
-                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
-            }
-            cp_async_commit();
-            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
-        }
-        const Stage<CH>& st = stages[b & 1];
-        const int* sid = s_id[b & 1];
-        const int cnt = min(BL_BATCH, maxc - b * BL_BATCH);
-        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
-        if (pos0 - (cnt - 1) >= wmax) continue;    // whole batch lies beyond every pixel of this warp
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-            bool hit = false;
-            if (k0 + lane < cnt) {
-                const float4 r0 = st.rec[2 * (k0 + lane)];
-                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
-                                  (r0.y - r1.w > wy1);
-                hit = !miss && (pos0 - (k0 + lane) < wmax);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = k0 + __ffs(m) - 1;
-                m &= m - 1;
-                const float4 r0 = st.rec[2 * j];
-                const float4 r1 = st.rec[2 * j + 1];
-                const int pos = pos0 - j;
-                float v[NV];
-#pragma unroll
-                for (int i = 0; i < NV; ++i) v[i] = 0.f;
-                bool valid = false;
-                if (pos < lc) {  // alpha_blending.cu:185-187
-                    const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
-                    const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
-                    float G, alpha;
-                    if (pair_alpha(power, r1.y, G, alpha)) {
-                        valid = true;
-                        const float rinv = rcp_approx(1.0f - alpha);
-                        T = T * rinv;  // :205
-                        const float wgt = alpha * T;
-                        const float om = 1.0f - last_alpha;
-                        float dL_dalpha = 0.f;
-                        const float* f = &st.feat[j * CH];
-#pragma unroll
-                        for (int k = 0; k < CH; ++k) {
-                            const float fk = f[k];
-                            accum[k] = fmaf(lastf[k], last_alpha, om * accum[k]);  // :213-214
-                            lastf[k] = fk;
-                            dL_dalpha = fmaf(fk - accum[k], dpix[k], dL_dalpha);   // :217
-                            v[6 + k] = wgt * dpix[k];                              // :218-219
-                        }
-                        dL_dalpha = fmaf(dL_dalpha, T, (-T_final * rinv) * bgdot);  // :222-229
-                        last_alpha = alpha;
-                        const float dL_dG = r1.y * dL_dalpha;  // :231
-                        const float gdl = G * dL_dG;
-                        v[0] = gdl * (-dx * r0.z - dy * r0.w);  // :232-237
-                        v[1] = gdl * (-dy * r1.x - dx * r0.w);
-                        v[2] = -0.5f * gdl * dx * dx;            // :238-242
-                        v[3] = -gdl * dx * dy;
-                        v[4] = -0.5f * gdl * dy * dy;
-                        v[5] = G * dL_dalpha;                    // :243
-                    }
-                }
-                if (__any_sync(0xffffffffu, valid)) {
-                    WarpRed<NV, 16>::run(v, upper);
-                    if (gptr != nullptr && v[0] != 0.f) atomicAdd(gptr + (long long)sid[j] * gstride, v[0]);
-                }
-            }
-        }
-    }
-    cp_async_wait<0>();
-}
-
-
-// ================================================================================================
-// v2 kernels: branch-free pair math + deferred shared-memory gradient reduction
-// ================================================================================================
-// Forward.  Same traversal as v1; the per-pair body has no divergent branches: a pair that fails
-// a test blends with weight 0 (ffma(T, 0 * f, F) == F), so the image is bit-identical to v1 and
-// to the reference, and a warp-visit costs ~40 instead of ~64 issue slots.
+// The per-pair body has no divergent branches: a pair that fails a test blends with weight 0
+// (ffma(T, 0 * f, F) == F), so the image is bit-identical to a branching formulation and to the
+// reference, and a warp-visit costs ~40 issue slots.
 template <int CH>
 __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
@@ -519,8 +205,10 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
     }
 }
 
-// Backward.  Per warp-visit every lane produces NV = 6 + CH gradient contributions.  v1 reduced
-// them across the warp with a transposing butterfly (~68 issue slots per visit).  v2 parks them
+// ------------------------------------------------------------------------------------------------
+// backward, v2 (kept behind MSB_BWD_V2=1 for A/B runs; the default is blend_bwd_kernel below)
+// ------------------------------------------------------------------------------------------------
+// Per warp-visit every lane produces NV = 6 + CH gradient contributions.  v2 parks them
 // in a per-warp shared-memory buffer [K visits][NV values][32 lanes] (row stride 36 floats:
 // conflict-free for the column writes and for the 16-byte row reads) and, every K visits, lane r
 // sums row r with 8 LDS.128 and issues one red.global: ~25 issue slots per visit.  The pair body
@@ -537,7 +225,7 @@ struct BwdRed {
 };
 
 template <int CH, int KV>
-__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v2(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
@@ -730,14 +418,290 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, v3: pixel-parallel replay + Gaussian-parallel gradient accumulation
+// ------------------------------------------------------------------------------------------------
+// Every gradient of a (pixel p, Gaussian g) pair is a product of two scalars that need the
+// sequential per-pixel replay,
+//     X(g,p) = G dL/dalpha            (alpha_blending.cu:222-231, 243)
+//     w(g,p) = alpha T                (:218-219)
+// with factors that depend only on g and on the pixel position:
+//     dL/dopacity = sum_p X                        dL/dfeature_k = sum_p w dpix_k(p)
+//     dL/du = -o (cx sum X dx + cy sum X dy)       dL/dv = -o (cz sum X dy + cy sum X dx)
+//     dL/dconic = -o (0.5 sum X dx^2, sum X dx dy, 0.5 sum X dy^2)         (:232-242)
+// Phase 1 (lane = pixel, as in the forward): replay the visits back to front and park (X, w) of
+// each visit in a per-warp shared-memory matrix [GQ Gaussians][32 pixels] (one STS.64 per visit).
+// Phase 2 (lane = Gaussian, every GQ = 16 visits): lane (g, h) walks 16 of the 32 pixels of
+// Gaussian g's row and accumulates the six moments and CH feature sums IN REGISTERS; the two
+// halves are combined with one shuffle per value and leave the SM as three vector reductions
+// (red.global.add.v4/.v2) per Gaussian.  No cross-lane reduction per visit, 10 instead of 26
+// shared-memory wavefronts per visit, ~75 instead of ~114 issue slots per visit (CH = 4).
+constexpr int BW_GQ = 16;  // Gaussians per phase-2 group
+constexpr int BW_PS = 33;  // row stride of the (X, w) matrix in float2: conflict-free LDS.64 in both phases
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+template <int CH>
+struct Bwd3 {
+    static constexpr size_t XW_BYTES = (size_t)(BL_NT / 32) * BW_GQ * BW_PS * sizeof(float2);
+    static constexpr size_t DPIX_BYTES = (size_t)BL_NT * CH * sizeof(float);
+    static constexpr size_t Q_BYTES = (size_t)(BL_NT / 32) * BW_GQ * sizeof(int);
+    static constexpr size_t SMEM = 2 * sizeof(Stage<CH>) + XW_BYTES + DPIX_BYTES + Q_BYTES;
+};
+
+// phase 2 for the first n (<= BW_GQ) parked visits of this warp
+template <int CH>
+__device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH>& st, const int* __restrict__ sid,
+                                                 const int* __restrict__ qw, const float2* __restrict__ xw,
+                                                 const float* __restrict__ dpw, float wx0, float wy0,
+                                                 float* __restrict__ grec, float* __restrict__ gfeat, int fstride,
+                                                 int foff, int geom_grads) {
+    __syncwarp();
+    const int g = lane & (BW_GQ - 1), h = lane >> 4;
+    float m0 = 0.f, mxy = 0.f;
+    f32x2 m1 = pk2(0.f, 0.f), m2 = pk2(0.f, 0.f);  // (sum X dx, sum X dy), (sum X dx^2, sum X dy^2)
+    f32x2 fs[CH / 2];
+#pragma unroll
+    for (int k = 0; k < CH / 2; ++k) fs[k] = pk2(0.f, 0.f);
+    float cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f;
+    int id = 0;
+    if (g < n) {
+        const int j = qw[g];
+        const float4 r0 = st.rec[2 * j];
+        const float4 r1 = st.rec[2 * j + 1];
+        id = sid[j];
+        cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y;
+        const float ux = r0.x - wx0;                       // dx of pixel column i: ux - i
+        const float dy0 = r0.y - (wy0 + (float)(2 * h));   // rows 2h and 2h+1 of the 8x4 block
+        const float dy1 = dy0 - 1.0f;
+        const float2* row = xw + g * BW_PS + h * 16;
+        const float4* dp = reinterpret_cast<const float4*>(dpw + h * 16 * CH);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float2 v = row[q];
+            const float dx = ux - (float)(q & 7);
+            const float dy = (q >> 3) ? dy1 : dy0;
+            const f32x2 d2 = pk2(dx, dy);
+            const f32x2 xd = mul2(pk2(v.x, v.x), d2);  // (X dx, X dy)
+            m1 = add2(m1, xd);
+            m2 = fma2(xd, d2, m2);
+            float xdx, xdy;
+            upk2(xd, xdx, xdy);
+            mxy = fmaf(xdx, dy, mxy);
+            m0 += v.x;
+            const f32x2 w2 = pk2(v.y, v.y);
+#pragma unroll
+            for (int k = 0; k < CH; k += 4) {
+                const float4 d = dp[q * (CH / 4) + k / 4];
+                fs[k / 2] = fma2(w2, pk2(d.x, d.y), fs[k / 2]);
+                fs[k / 2 + 1] = fma2(w2, pk2(d.z, d.w), fs[k / 2 + 1]);
+            }
+        }
+    }
+    // combine the two pixel halves (every lane takes part; idle lanes hold zeros)
+    float mx, my, mxx, myy;
+    upk2(m1, mx, my);
+    upk2(m2, mxx, myy);
+    m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+    mx += __shfl_xor_sync(0xffffffffu, mx, 16);
+    my += __shfl_xor_sync(0xffffffffu, my, 16);
+    mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
+    mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
+    myy += __shfl_xor_sync(0xffffffffu, myy, 16);
+    float f[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k += 2) {
+        upk2(fs[k / 2], f[k], f[k + 1]);
+        f[k] += __shfl_xor_sync(0xffffffffu, f[k], 16);
+        f[k + 1] += __shfl_xor_sync(0xffffffffu, f[k + 1], 16);
+    }
+    if (g < n) {
+        if (h == 0) {
+            if (geom_grads) {
+                const float nop = -op;
+                float* gp = grec + (long long)id * 8;
+                red_add_v4(gp, nop * fmaf(cx, mx, cy * my), nop * fmaf(cz, my, cy * mx), 0.5f * nop * mxx, nop * mxy);
+                red_add_v2(gp + 4, 0.5f * nop * myy, m0);
+            }
+        } else {
+            float* fp = gfeat + (long long)id * fstride + foff;
+#pragma unroll
+            for (int k = 0; k < CH; k += 4) red_add_v4(fp + k, f[k], f[k + 1], f[k + 2], f[k + 3]);
+        }
+    }
+    __syncwarp();
+}
+
+template <int CH>
+__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+                                                          const float* __restrict__ featp, int fstride, int foff,
+                                                          const int* __restrict__ ids,
+                                                          const int2* __restrict__ tile_range, float bg,
+                                                          int c_valid, int W, int H,
+                                                          const float* __restrict__ final_T,
+                                                          const int* __restrict__ ncontrib,
+                                                          const float* __restrict__ dL_dimage,
+                                                          float* __restrict__ grec, float* __restrict__ gfeat,
+                                                          int geom_grads) {
+    extern __shared__ __align__(16) unsigned char bl_raw[];
+    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
+    float2* s_xw = reinterpret_cast<float2*>(bl_raw + 2 * sizeof(Stage<CH>));
+    float* s_dpix = reinterpret_cast<float*>(bl_raw + 2 * sizeof(Stage<CH>) + Bwd3<CH>::XW_BYTES);
+    int* s_q = reinterpret_cast<int*>(bl_raw + 2 * sizeof(Stage<CH>) + Bwd3<CH>::XW_BYTES + Bwd3<CH>::DPIX_BYTES);
+    __shared__ int s_id[2][BL_BATCH];
+    __shared__ int s_max[BL_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
+    const int tile = blockIdx.y * gxt + blockIdx.x;
+    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const bool inside = px < W && py < H;
+    const long long pix = (long long)py * W + px;
+    const long long hw = (long long)H * W;
+
+    const int2 range = tile_range[tile];
+    const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
+    int wmax = lc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    f32x2 dpix2[CH / 2], S2[CH / 2];  // cotangent and suffix colour, two channels per 64-bit register pair
+    float bgdot = 0.f;
+    float* dpw = s_dpix + warp * 32 * CH;  // this warp's cotangents, [pixel][channel]
+    {
+        float dpix[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
+            bgdot = fmaf(bg, dpix[k], bgdot);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k += 2) {
+            dpix2[k / 2] = pk2(dpix[k], dpix[k + 1]);
+            S2[k / 2] = pk2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k += 4)
+            *reinterpret_cast<float4*>(dpw + lane * CH + k) = make_float4(dpix[k], dpix[k + 1], dpix[k + 2], dpix[k + 3]);
+    }
+    __syncthreads();
+    int maxc = 0;
+#pragma unroll
+    for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
+    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
+    const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
+
+    float2* xw = s_xw + warp * (BW_GQ * BW_PS);
+    int* qw = s_q + warp * BW_GQ;
+    float2* xw_wr = xw + lane;  // this lane's cell in the row of the next parked visit
+    int* qw_wr = qw;            // its slot index (warp-uniform pointer; every lane stores the same value)
+    int cnt = 0;                // parked visits (warp-uniform)
+
+    // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
+    int id_next = 0;
+    if (nb > 0) {
+        if (tid < maxc) {
+            const int id = ids[range.x + maxc - 1 - tid];
+            s_id[0][tid] = id;
+            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
+        }
+        cp_async_commit();
+        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
+    }
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (b + 1 < nb) {
+            if ((b + 1) * BL_BATCH + tid < maxc) {
+                s_id[(b + 1) & 1][tid] = id_next;
+                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            }
+            cp_async_commit();
+            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
+        }
+        const Stage<CH>& st = stages[b & 1];
+        const int* sid = s_id[b & 1];
+        const int bcnt = min(BL_BATCH, maxc - b * BL_BATCH);
+        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
+        if (pos0 - (bcnt - 1) >= wmax) continue;   // whole batch lies beyond every pixel of this warp
+        for (int k0 = 0; k0 < bcnt; k0 += 32) {
+            bool hit = false;
+            if (k0 + lane < bcnt) {
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
+                                  (r0.y - r1.w > wy1);
+                hit = !miss && (pos0 - (k0 + lane) < wmax);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 r0 = st.rec[2 * j];
+                const float4 r1 = st.rec[2 * j + 1];
+                const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
+                const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
+                const float Graw = ex2_approx(fmul(power, kLog2e));
+                const float araw = fmin_ftz(fmul(r1.y, Graw), kAlphaMax);
+                // alpha_blending.cu:185-187 (pos < lc) and :190-203 (power / alpha tests)
+                const bool valid = (pos0 - j < lc) && !(power > 0.0f) && !(araw < kAlphaMin);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                const float alpha = valid ? araw : 0.0f;
+                const float G = valid ? Graw : 0.0f;
+                const float rinv = rcp_approx(1.0f - alpha);  // == 1 for a failing pair
+                T = T * rinv;                                  // :205
+                const float wgt = alpha * T;
+                // channel math on packed pairs (FFMA2/FMUL2): per pair of channels
+                //   e = f T - S / (1 - alpha);  dL_dalpha += e . dpix;  S += f alpha T
+                const f32x2 T2 = pk2(T, T), W2 = pk2(wgt, wgt), NR2 = pk2(-rinv, -rinv);
+                f32x2 dacc = pk2(nbg * rinv, 0.f);             // :222-229 (background term)
+#pragma unroll
+                for (int k = 0; k < CH; k += 4) {
+                    const float4 fv = *reinterpret_cast<const float4*>(&st.feat[j * CH + k]);
+                    const f32x2 fa = pk2(fv.x, fv.y), fb = pk2(fv.z, fv.w);
+                    const f32x2 ea = fma2(S2[k / 2], NR2, mul2(fa, T2));           // :213-217
+                    const f32x2 eb = fma2(S2[k / 2 + 1], NR2, mul2(fb, T2));
+                    dacc = fma2(ea, dpix2[k / 2], dacc);
+                    dacc = fma2(eb, dpix2[k / 2 + 1], dacc);
+                    S2[k / 2] = fma2(fa, W2, S2[k / 2]);
+                    S2[k / 2 + 1] = fma2(fb, W2, S2[k / 2 + 1]);
+                }
+                float dlo, dhi;
+                upk2(dacc, dlo, dhi);
+                *xw_wr = make_float2(G * (dlo + dhi), wgt);  // (X, w) of this pair
+                xw_wr += BW_PS;
+                *qw_wr++ = j;
+                if (++cnt == BW_GQ) {
+                    bwd_reduce_group<CH>(BW_GQ, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
+                                         geom_grads);
+                    cnt = 0;
+                    xw_wr = xw + lane;
+                    qw_wr = qw;
+                }
+            }
+        }
+        if (cnt > 0) {  // the stage buffer is recycled after this batch
+            bwd_reduce_group<CH>(cnt, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff, geom_grads);
+            cnt = 0;
+            xw_wr = xw + lane;
+            qw_wr = qw;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 static inline int pick_fwd_ch(int rem) { return rem >= 32 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4; }
 static inline int pick_bwd_ch(int rem) { return rem >= 16 ? 16 : rem > 4 ? 8 : 4; }
-
-// temporary A/B switch for profiling: MSB_BLEND_V1=1 selects the v1 kernels
-static bool blend_use_v1() {
-    static const int v = [] { const char* e = getenv("MSB_BLEND_V1"); return (e && e[0] == '1') ? 1 : 0; }();
-    return v != 0;
-}
 
 template <int CH>
 static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
@@ -749,20 +713,15 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
                                              (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_fwd: cudaFuncSetAttribute failed");
     }
-    if (blend_use_v1()) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(blend_fwd_kernel_v1<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        blend_fwd_kernel_v1<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                           write_aux, final_T, ncontrib, image);
-        return check_launch("alpha_blending_fwd");
-    }
     blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
                                                     final_T, ncontrib, image);
     return check_launch("alpha_blending_fwd");
 }
 
-static int bwd_k_override() {
-    static const int v = [] { const char* e = getenv("MSB_BWD_K"); return e ? atoi(e) : 0; }();
-    return v;
+// A/B switch for profiling runs: MSB_BWD_V2=1 selects the v2 backward kernel
+static bool blend_use_bwd_v2() {
+    static const int v = [] { const char* e = getenv("MSB_BWD_V2"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v != 0;
 }
 
 template <int CH, int KV>
@@ -771,12 +730,12 @@ static int launch_bwd_v2(dim3 grid, cudaStream_t st, const float4* rec, const fl
                          const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
     const size_t smem = 2 * sizeof(Stage<CH>) + (size_t)(BL_NT / 32) * BwdRed<CH, KV>::FLOATS * sizeof(float);
     if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel_v2<CH, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
     }
-    blend_bwd_kernel<CH, KV><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
-                                                        ncontrib, dL_dimage, grec, gfeat, geom);
+    blend_bwd_kernel_v2<CH, KV><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                           final_T, ncontrib, dL_dimage, grec, gfeat, geom);
     return check_launch("alpha_blending_bwd");
 }
 
@@ -784,20 +743,20 @@ template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
                       const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
-    if (blend_use_v1()) {
-        const size_t smem1 = 2 * sizeof(Stage<CH>);
-        if (smem1 > 40 * 1024) cudaFuncSetAttribute(blend_bwd_kernel_v1<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        blend_bwd_kernel_v1<CH><<<grid, BL_NT, smem1, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                            final_T, ncontrib, dL_dimage, grec, gfeat, geom);
-        return check_launch("alpha_blending_bwd");
+    if (blend_use_bwd_v2()) {
+        constexpr int KV = CH == 4 ? 2 : 32 / (6 + CH);
+        return launch_bwd_v2<CH, KV>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib,
+                                     dL_dimage, grec, gfeat, geom);
     }
-    constexpr int KDEF = 32 / (6 + CH);
-    // CH = 4: K = 2 keeps the CTA at 48 KB of shared memory (4 CTAs/SM); K = 3 (59 KB, 3 CTAs/SM) measured 2.5 % slower
-    if (CH == 4 && bwd_k_override() != 3)
-        return launch_bwd_v2<CH, (CH == 4 ? 2 : KDEF)>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                      final_T, ncontrib, dL_dimage, grec, gfeat, geom);
-    return launch_bwd_v2<CH, KDEF>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib,
-                                   dL_dimage, grec, gfeat, geom);
+    const size_t smem = Bwd3<CH>::SMEM;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    }
+    blend_bwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
+                                                    ncontrib, dL_dimage, grec, gfeat, geom);
+    return check_launch("alpha_blending_bwd");
 }
 
 // channel-chunk dispatcher of the forward pass (reference D1: alpha_blending.cu:248-394)
