@@ -367,6 +367,17 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
         stages[name] = st
     dom = next(iter(stages))
     roof = {"kernel": dom}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of each call's kernel(s), from the committed
+    # `ncu --set full` capture of this same workload (profiles/ncu_traffic.json; null for other sizes)
+    traffic = {}
+    if (P, W, H) == (P_FULL, W_FULL, H_FULL):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            traffic = {}
+    for name, st in stages.items():
+        if isinstance(traffic.get(name), (int, float)):
+            st["dram_traffic_MB"] = round(traffic[name] / 1e6, 1)
     if is_blend(dom):
         bwd = dom.endswith("backward")
         lane_ops = (32 + 5 * C) if bwd else (13 + C)
@@ -374,7 +385,7 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
         peak = min(sms * 128 * f_hz / lane_ops, sms * 16 * f_hz / mufu) / 1e9
         ach = stages[dom]["Gpairs_per_s"]
         roof.update({"bound": "fp32_issue", "achieved": ach, "peak": round(peak, 1), "unit": "Gpairs/s",
-                     "frac": round(ach / peak, 4), "traffic": None,
+                     "frac": round(ach / peak, 4), "traffic": traffic.get(dom),
                      "note": f"pair = sum(ncontrib) = {pairs} per render (SURVEY 8d); peak = min(SMs*128*f/"
                              f"{lane_ops} lane-ops, SMs*16*f/{mufu} MUFU) at {sms} SMs, f = {f_hz/1e6:.0f} MHz "
                              f"(clock observed during the run); not an HBM/tensor kernel: DRAM traffic is <10% of "
@@ -382,7 +393,7 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
     else:
         ach = stages[dom].get("GBps", 0.0)
         roof.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
-                     "traffic": None, "note": f"peak: {src}"})
+                     "traffic": traffic.get(dom), "note": f"peak: {src}"})
     # secondary: the HBM-bound sort (the north star asks for its achieved GB/s)
     if "sort_gaussian" in stages:
         s = stages["sort_gaussian"]

@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(256) blend_unpack_kernel(int P, int C, int Cpa
 // ------------------------------------------------------------------------------------------------
 // shared-memory stage: 256 records + 256 feature rows
 // ------------------------------------------------------------------------------------------------
-template <int CH>
+template <int CH, int B = BL_BATCH>
 struct Stage {
-    float4 rec[BL_BATCH * 2];
-    float feat[BL_BATCH * CH];
+    float4 rec[B * 2];
+    float feat[B * CH];
 };
 
-template <int CH>
-__device__ __forceinline__ void stage_issue(Stage<CH>& st, int slot, int id, const float4* __restrict__ rec,
+template <int CH, int B>
+__device__ __forceinline__ void stage_issue(Stage<CH, B>& st, int slot, int id, const float4* __restrict__ rec,
                                             const float* __restrict__ featp, int fstride, int foff) {
     const float4* r = rec + 2 * (long long)id;
     cp_async16(&st.rec[2 * slot], r);
@@ -125,13 +125,13 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
 
     float T = 1.0f;
     int last = 0;
-    f32x2 F2[CH / 2];  // accumulated colour, two channels per 64-bit register pair (FFMA2)
+    float F[CH];  // accumulated colour
 #pragma unroll
-    for (int k = 0; k < CH / 2; ++k) F2[k] = pk2(0.f, 0.f);
+    for (int k = 0; k < CH; ++k) F[k] = 0.f;
 
     int id_next = 0;
     if (nb > 0) {
-        if (tid < n) stage_issue<CH>(stages[0], tid, ids[range.x + tid], rec, featp, fstride, foff);
+        if (tid < n) stage_issue(stages[0], tid, ids[range.x + tid], rec, featp, fstride, foff);
         cp_async_commit();
         if (BL_BATCH + tid < n) id_next = ids[range.x + BL_BATCH + tid];
     }
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
         if (__syncthreads_and(done)) break;
         if (b + 1 < nb) {
             if ((b + 1) * BL_BATCH + tid < n)
-                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+                stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
             cp_async_commit();
             if ((b + 2) * BL_BATCH + tid < n) id_next = ids[range.x + (b + 2) * BL_BATCH + tid];
         }
@@ -174,12 +174,17 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
                 done = done || term;
                 const float a = blend ? alpha : 0.0f;
                 const float* f = &st.feat[j * CH];
-                const f32x2 a2 = pk2(a, a), T2 = pk2(T, T);
+                const f32x2 a2 = pk2(a, a);
 #pragma unroll
                 for (int k = 0; k < CH; k += 4) {  // F_k = fma(T, alpha * f_k, F_k), same rounding as the scalar ops
                     const float4 fv = *reinterpret_cast<const float4*>(f + k);
-                    F2[k / 2] = fma2(T2, mul2(a2, pk2(fv.x, fv.y)), F2[k / 2]);
-                    F2[k / 2 + 1] = fma2(T2, mul2(a2, pk2(fv.z, fv.w)), F2[k / 2 + 1]);
+                    float p0, p1, p2, p3;
+                    upk2(mul2(a2, pk2(fv.x, fv.y)), p0, p1);  // packed products, scalar accumulation: the
+                    upk2(mul2(a2, pk2(fv.z, fv.w)), p2, p3);  // loop-carried FFMA2 pairs cost a MOV per register
+                    F[k] = ffma(T, p0, F[k]);
+                    F[k + 1] = ffma(T, p1, F[k + 1]);
+                    F[k + 2] = ffma(T, p2, F[k + 2]);
+                    F[k + 3] = ffma(T, p3, F[k + 3]);
                 }
                 T = blend ? nT : T;
                 last = blend ? base1 + j : last;
@@ -196,12 +201,8 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
         }
         const long long hw = (long long)H * W;
 #pragma unroll
-        for (int k = 0; k < CH; k += 2) {
-            float f0, f1;
-            upk2(F2[k / 2], f0, f1);
-            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, f0);
-            if (k + 1 < c_valid) image[(k + 1) * hw + pix] = ffma(T, bg, f1);
-        }
+        for (int k = 0; k < CH; ++k)
+            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
     }
 }
 
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v2(const float4* __res
         if (tid < maxc) {
             const int id = ids[range.x + maxc - 1 - tid];
             s_id[0][tid] = id;
-            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
+            stage_issue(stages[0], tid, id, rec, featp, fstride, foff);
         }
         cp_async_commit();
         if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v2(const float4* __res
         if (b + 1 < nb) {
             if ((b + 1) * BL_BATCH + tid < maxc) {
                 s_id[(b + 1) & 1][tid] = id_next;
-                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+                stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
             }
             cp_async_commit();
             if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
@@ -446,17 +447,18 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
-template <int CH>
+template <int CH, int B>
 struct Bwd3 {
+    static constexpr size_t STAGE_BYTES = 2 * sizeof(Stage<CH, B>);
     static constexpr size_t XW_BYTES = (size_t)(BL_NT / 32) * BW_GQ * BW_PS * sizeof(float2);
     static constexpr size_t DPIX_BYTES = (size_t)BL_NT * CH * sizeof(float);
     static constexpr size_t Q_BYTES = (size_t)(BL_NT / 32) * BW_GQ * sizeof(int);
-    static constexpr size_t SMEM = 2 * sizeof(Stage<CH>) + XW_BYTES + DPIX_BYTES + Q_BYTES;
+    static constexpr size_t SMEM = STAGE_BYTES + XW_BYTES + DPIX_BYTES + Q_BYTES;
 };
 
 // phase 2 for the first n (<= BW_GQ) parked visits of this warp
-template <int CH>
-__device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH>& st, const int* __restrict__ sid,
+template <int CH, int B>
+__device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH, B>& st, const int* __restrict__ sid,
                                                  const int* __restrict__ qw, const float2* __restrict__ xw,
                                                  const float* __restrict__ dpw, float wx0, float wy0,
                                                  float* __restrict__ grec, float* __restrict__ gfeat, int fstride,
@@ -537,8 +539,8 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
     __syncwarp();
 }
 
-template <int CH>
-__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restrict__ rec,
+template <int CH, int B, int MINB>
+__global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
@@ -549,11 +551,12 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
                                                           float* __restrict__ grec, float* __restrict__ gfeat,
                                                           int geom_grads) {
     extern __shared__ __align__(16) unsigned char bl_raw[];
-    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
-    float2* s_xw = reinterpret_cast<float2*>(bl_raw + 2 * sizeof(Stage<CH>));
-    float* s_dpix = reinterpret_cast<float*>(bl_raw + 2 * sizeof(Stage<CH>) + Bwd3<CH>::XW_BYTES);
-    int* s_q = reinterpret_cast<int*>(bl_raw + 2 * sizeof(Stage<CH>) + Bwd3<CH>::XW_BYTES + Bwd3<CH>::DPIX_BYTES);
-    __shared__ int s_id[2][BL_BATCH];
+    using L = Bwd3<CH, B>;
+    Stage<CH, B>* stages = reinterpret_cast<Stage<CH, B>*>(bl_raw);
+    float2* s_xw = reinterpret_cast<float2*>(bl_raw + L::STAGE_BYTES);
+    float* s_dpix = reinterpret_cast<float*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES);
+    int* s_q = reinterpret_cast<int*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES + L::DPIX_BYTES);
+    __shared__ int s_id[2 * B];  // [2][B] Gaussian ids of the staged slots
     __shared__ int s_max[BL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
     int maxc = 0;
 #pragma unroll
     for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
-    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
+    const int nb = (maxc + B - 1) / B;
     const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
 
     float2* xw = s_xw + warp * (BW_GQ * BW_PS);
@@ -610,29 +613,29 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
     // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
     int id_next = 0;
     if (nb > 0) {
-        if (tid < maxc) {
+        if (tid < B && tid < maxc) {
             const int id = ids[range.x + maxc - 1 - tid];
-            s_id[0][tid] = id;
-            stage_issue<CH>(stages[0], tid, id, rec, featp, fstride, foff);
+            s_id[tid] = id;
+            stage_issue(stages[0], tid, id, rec, featp, fstride, foff);
         }
         cp_async_commit();
-        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
+        if (tid < B && B + tid < maxc) id_next = ids[range.x + maxc - 1 - (B + tid)];
     }
     for (int b = 0; b < nb; ++b) {
         cp_async_wait<0>();
         __syncthreads();
         if (b + 1 < nb) {
-            if ((b + 1) * BL_BATCH + tid < maxc) {
-                s_id[(b + 1) & 1][tid] = id_next;
-                stage_issue<CH>(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
+            if (tid < B && (b + 1) * B + tid < maxc) {
+                s_id[((b + 1) & 1) * B + tid] = id_next;
+                stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
             }
             cp_async_commit();
-            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
+            if (tid < B && (b + 2) * B + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * B + tid)];
         }
-        const Stage<CH>& st = stages[b & 1];
-        const int* sid = s_id[b & 1];
-        const int bcnt = min(BL_BATCH, maxc - b * BL_BATCH);
-        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
+        const Stage<CH, B>& st = stages[b & 1];
+        const int* sid = s_id + (b & 1) * B;
+        const int bcnt = min(B, maxc - b * B);
+        const int pos0 = maxc - 1 - b * B;  // list position of slot 0 of this batch
         if (pos0 - (bcnt - 1) >= wmax) continue;   // whole batch lies beyond every pixel of this warp
         for (int k0 = 0; k0 < bcnt; k0 += 32) {
             bool hit = false;
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
                 xw_wr += BW_PS;
                 *qw_wr++ = j;
                 if (++cnt == BW_GQ) {
-                    bwd_reduce_group<CH>(BW_GQ, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
+                    bwd_reduce_group<CH, B>(BW_GQ, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
                                          geom_grads);
                     cnt = 0;
                     xw_wr = xw + lane;
@@ -691,7 +694,7 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel(const float4* __restri
             }
         }
         if (cnt > 0) {  // the stage buffer is recycled after this batch
-            bwd_reduce_group<CH>(cnt, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff, geom_grads);
+            bwd_reduce_group<CH, B>(cnt, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff, geom_grads);
             cnt = 0;
             xw_wr = xw + lane;
             qw_wr = qw;
@@ -739,6 +742,31 @@ static int launch_bwd_v2(dim3 grid, cudaStream_t st, const float4* rec, const fl
     return check_launch("alpha_blending_bwd");
 }
 
+// A/B switch for profiling runs (CH = 4).  Measured on BASELINE config #3 (profiles/r1_ab_blend_bwd.md):
+//   default  256-entry batches, compiler's register count (80 -> 3 CTAs/SM)   1.064 ms
+//   1        128-entry batches, 80 registers (3 CTAs/SM)                      1.111 ms
+//   3        128-entry batches, 64 registers (4 CTAs/SM, 40 B of spills)      1.150 ms
+// Fewer barriers per list entry beat the extra resident CTA.
+static int blend_bwd_cfg() {
+    static const int v = [] { const char* e = getenv("MSB_BWD_CFG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <int CH, int B, int MINB>
+static int launch_bwd_cfg(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
+                          const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
+                          const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
+    const size_t smem = Bwd3<CH, B>::SMEM;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    }
+    blend_bwd_kernel<CH, B, MINB><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                             final_T, ncontrib, dL_dimage, grec, gfeat, geom);
+    return check_launch("alpha_blending_bwd");
+}
+
 template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
@@ -748,15 +776,17 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float
         return launch_bwd_v2<CH, KV>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib,
                                      dL_dimage, grec, gfeat, geom);
     }
-    const size_t smem = Bwd3<CH>::SMEM;
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+#define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, grec, gfeat, geom
+    if constexpr (CH == 4) {
+        switch (blend_bwd_cfg()) {
+            case 1: return launch_bwd_cfg<CH, 128, 0>(MSB_BWD_ARGS);
+            case 3: return launch_bwd_cfg<CH, 128, 4>(MSB_BWD_ARGS);
+            default: return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
+        }
+    } else {
+        return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
     }
-    blend_bwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
-                                                    ncontrib, dL_dimage, grec, gfeat, geom);
-    return check_launch("alpha_blending_bwd");
+#undef MSB_BWD_ARGS
 }
 
 // channel-chunk dispatcher of the forward pass (reference D1: alpha_blending.cu:248-394)

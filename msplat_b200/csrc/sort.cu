@@ -20,21 +20,27 @@
 // Gaussian-index order, exactly like the stable sort of the slots.  Never-written slots are
 // all (key 0, idx 0) and therefore form a prefix of tile 0: they are emitted first.
 //
-// Pipeline (all integer work, HBM-bound):
+// Pipeline (all integer work):
 //   phase 1  count     : M = sum(max(tiles,0)) -> pinned host memory (sizes the output)
-//   phase 2a keygen    : per Gaussian: emitted-entry count n, depth key (0xFFFFFFFF if n == 0),
-//                        digit histograms of the 4 depth passes, phantom-slot count Z
-//   phase 2b onesweep  : 4 passes of 8 bits over (depth key, Gaussian id), P elements; each pass is
-//                        ONE kernel: warp-ballot (match.any) ranking into shared-memory histograms,
-//                        chained scan with decoupled look-back on a (value|flag) word per digit,
-//                        keys exchanged through shared memory so global writes are coalesced
-//   phase 2c offsets   : exclusive scan of n in depth order (+Z)
+//   phase 2a keygen    : the Pc Gaussians that emit at least one entry are compacted (index order
+//                        kept, no chained scan) into (depth key, id) pairs; per Gaussian a 16-byte
+//                        record {x0, y0, w, n} of its tile rectangle; digit histograms of the 4 depth
+//                        passes; phantom-slot count Z.  Pc stays on the device.
+//   phase 2b onesweep  : 4 passes of 8 bits over (depth key, Gaussian id), Pc elements, L2-resident;
+//                        each pass is ONE kernel: ballot-built peer masks -> ranks in shared-memory
+//                        histograms, chained scan with decoupled look-back on a (value|flag) word per
+//                        digit, keys exchanged through shared memory so global writes are coalesced
+//   phase 2c offsets   : single-pass chained exclusive scan of n in depth order (+Z)
 //   phase 2d duplicate : warp-cooperative emission of (tile id, Gaussian id) in depth order; the
 //                        histograms of the tile passes are accumulated on the fly
-//   phase 2e onesweep  : ceil(bits(T-1)/8) passes over (tile id, Gaussian id), M elements
+//   phase 2e onesweep  : ceil(bits(T-1)/8) passes over (tile id, Gaussian id), M elements; the top
+//                        digit compares only the bits the tile ids use
 //   phase 2f ranges    : boundary detection on the sorted tile ids
-// Algorithmic bytes: 24 B/Gaussian keygen + 4 * 16 B/Gaussian + 24 B/Gaussian offsets/duplicate reads
-//                    + 8 B/key duplicate write + pt * 16 B/key + 4 B/key ranges.
+// Algorithmic bytes: 20 B/Gaussian keygen reads (+20 again from L2) + per emitter 8 B pair + 16 B
+//                    record, 4 * 16 B/emitter depth passes, 28 B/emitter offsets + duplicate reads,
+//                    8 B/key duplicate write + pt * 16 B/key + 4 B/key ranges.
+#include <stdlib.h>
+
 #include "geom.cuh"
 
 namespace msb {
@@ -76,13 +82,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp /*[NTH/32 + 1]
     return res;
 }
 
-// value i of the scanned sequence: max(vals[i], 0), or vals[perm[i]] when a permutation is given
-__device__ __forceinline__ int scan_value(const int* __restrict__ vals, const int* __restrict__ perm, long long i) {
-    return perm != nullptr ? vals[perm[i]] : max(vals[i], 0);
-}
+// value i of the scanned sequence
+__device__ __forceinline__ int scan_value(const int* __restrict__ vals, long long i) { return max(vals[i], 0); }
 
 __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int* __restrict__ vals,
-                                                                const int* __restrict__ perm,
                                                                 long long* __restrict__ bsum) {
     __shared__ long long s_part[SC_NT / 32];
     const long long base = (long long)blockIdx.x * SC_TILE;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k * SC_NT + threadIdx.x;
-        if (i < P) acc += scan_value(vals, perm, i);
+        if (i < P) acc += scan_value(vals, i);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -139,12 +142,10 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(int nb, long long* __r
     if (threadIdx.x == 0) *total_dev = carry;
 }
 
-// out[i] = (EXCL ? exclusive : inclusive) prefix of the sequence, plus *bias (if given)
+// out[i] = (EXCL ? exclusive : inclusive) prefix of the sequence
 template <bool EXCL>
 __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __restrict__ vals,
-                                                           const int* __restrict__ perm,
                                                            const long long* __restrict__ bsum,
-                                                           const unsigned int* __restrict__ bias,
                                                            int* __restrict__ out) {
     __shared__ int s_warp[SC_NT / 32 + 1];
     const long long base = (long long)blockIdx.x * SC_TILE + (long long)threadIdx.x * SC_IPT;
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k;
-        v[k] = i < P ? scan_value(vals, perm, i) : 0;
+        v[k] = i < P ? scan_value(vals, i) : 0;
         sum += v[k];
     }
     int total;
-    int run = block_excl_scan<SC_NT>(sum, s_warp, total) + (int)bsum[blockIdx.x] + (bias ? (int)*bias : 0);
+    int run = block_excl_scan<SC_NT>(sum, s_warp, total) + (int)bsum[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k;
@@ -172,53 +173,156 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2a: per-Gaussian depth key, emitted-entry count, depth-digit histograms
+// phase 2a: depth key + emitted-entry count of every Gaussian that emits, stably COMPACTED
 // ------------------------------------------------------------------------------------------------
+// Gaussians that emit no entry (culled, zero footprint; ~40 % of BASELINE config #3) are dropped
+// here instead of being carried through the four depth passes as 0xFFFFFFFF keys: the passes,
+// the offset scan and the duplication then run over Pc = #emitting Gaussians, a count that only
+// exists on the device (*pcount).  The output keeps Gaussian-index order (the stability of the
+// sort relies on it) without a chained scan: the grid is at most one wave of CTAs; virtual CTA v
+// (ticket order) owns the contiguous index range [v R, (v+1) R), each of its warps a contiguous
+// sub-range.  Pass A counts the emitters per warp; the CTA publishes (flag | count) and sums the
+// counts of the virtual CTAs before it -- all of which have started, so the wait is one round
+// trip, not a chain; pass B re-reads the range (L2 hits) and writes each warp's emitters at its
+// prefix with ballot ranks.
 constexpr int KG_NT = 256;
+constexpr int KG_WARPS = KG_NT / 32;
 constexpr int MAX_TPASS = 4;  // tile id < 2^31
+constexpr unsigned int RS_FLAG_AGG = 1u << 30;
+constexpr unsigned int RS_FLAG_PRE = 2u << 30;
+constexpr unsigned int RS_VALUE_MASK = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, const float2* __restrict__ uv,
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// emitted entries of a Gaussian (0 if it takes no part) and its tile rectangle
+__device__ __forceinline__ int keygen_count(int slots, int rad, float2 p, int gx, int gy, int& x0, int& y0, int& w) {
+    int n = 0;
+    x0 = y0 = 0;
+    w = 1;
+    if (rad > 0 && slots > 0) {  // sort_gaussian.cu:26
+        const Rect q = get_rect(p.x, p.y, rad, gx, gy);
+        n = min(max((q.x1 - q.x0) * (q.y1 - q.y0), 0), slots);
+        x0 = q.x0;
+        y0 = q.y0;
+        w = max(q.x1 - q.x0, 1);
+    }
+    return n;
+}
+
+constexpr int KG_ROWS = 4;  // rows of 32 Gaussians whose loads are issued together (memory-level parallelism)
+
+__global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int seg /*Gaussians per warp, multiple of 32*/,
+                                                       const float2* __restrict__ uv,
                                                        const float* __restrict__ depth,
                                                        const int* __restrict__ radius,
                                                        const int* __restrict__ tiles, int gx, int gy,
                                                        unsigned int* __restrict__ dkeys, int* __restrict__ dvals,
-                                                       int* __restrict__ cnt,
+                                                       int4* __restrict__ rect /*[P] {x0, y0, w, n} of the emitters*/,
                                                        unsigned int* __restrict__ hist /*[4][256]*/,
-                                                       unsigned int* __restrict__ zcount) {
+                                                       unsigned int* __restrict__ zcount,
+                                                       unsigned int* __restrict__ status /*[gridDim.x]*/,
+                                                       unsigned int* __restrict__ ticket,
+                                                       unsigned int* __restrict__ pcount) {
     __shared__ unsigned int s_hist[4 * 256];
+    __shared__ unsigned int s_wcnt[KG_WARPS];
+    __shared__ unsigned int s_part[KG_WARPS];
+    __shared__ int s_vcta;
     for (int i = threadIdx.x; i < 4 * 256; i += KG_NT) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_vcta = (int)atomicAdd(ticket, 1u);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    unsigned int zsum = 0;
-    const long long nchunks = ((long long)P + KG_NT - 1) / KG_NT;
-    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const long long i = chunk * KG_NT + threadIdx.x;
-        int n = 0;
-        unsigned int key = 0xffffffffu;
-        if (i < P) {
-            const int slots = max(tiles[i], 0);
-            const int rad = radius[i];
-            if (rad > 0 && slots > 0) {  // sort_gaussian.cu:26
-                const float2 c = uv[i];
-                const Rect q = get_rect(c.x, c.y, rad, gx, gy);
-                n = min(max((q.x1 - q.x0) * (q.y1 - q.y0), 0), slots);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vcta = s_vcta;
+    const long long w0 = ((long long)vcta * KG_WARPS + warp) * seg;
+    const long long w1 = min(w0 + seg, (long long)P);
+
+    // ---- pass A: emitters of this warp's range ---------------------------------------------------
+    unsigned int wcount = 0, zsum = 0;
+    for (long long i0 = w0; i0 < w1; i0 += 32 * KG_ROWS) {
+        int sl[KG_ROWS], rd[KG_ROWS];
+        float2 pp[KG_ROWS];
+#pragma unroll
+        for (int r = 0; r < KG_ROWS; ++r) {
+            const long long i = i0 + 32 * r + lane;
+            const bool in = i < w1;
+            sl[r] = in ? max(tiles[i], 0) : 0;
+            rd[r] = in ? radius[i] : 0;
+            pp[r] = in ? uv[i] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < KG_ROWS; ++r) {
+            int x0, y0, w;
+            const int n = keygen_count(sl[r], rd[r], pp[r], gx, gy, x0, y0, w);
+            zsum += (unsigned)(sl[r] - n);  // never-written slots stay (0, 0): sort_gaussian.cu:98-99
+            wcount += __popc(__ballot_sync(0xffffffffu, n > 0));
+        }
+    }
+    if (lane == 0) s_wcnt[warp] = wcount;
+    __syncthreads();
+    unsigned int wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < KG_WARPS; ++w) {
+        const unsigned int c = s_wcnt[w];
+        wpre += w < warp ? c : 0u;
+        total += c;
+    }
+    if (threadIdx.x == 0) st_relaxed(status + vcta, RS_FLAG_PRE | total);
+
+    // ---- prefix over the virtual CTAs before this one (all of them have started) -----------------
+    unsigned int part = 0;
+    for (int j = threadIdx.x; j < vcta; j += KG_NT) {
+        unsigned int v = ld_relaxed(status + j);
+        while (v == 0u) {
+            __nanosleep(20);
+            v = ld_relaxed(status + j);
+        }
+        part += v & RS_VALUE_MASK;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    unsigned int pos = wpre;
+#pragma unroll
+    for (int w = 0; w < KG_WARPS; ++w) pos += s_part[w];
+    if (threadIdx.x == 0 && vcta == (int)gridDim.x - 1) *pcount = pos + total;  // wpre == 0 for thread 0
+
+    // ---- pass B: compacted (depth key, id) pairs, rectangles, depth-digit histograms (L2 re-read) -
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (long long i0 = w0; i0 < w1; i0 += 32 * KG_ROWS) {
+        int sl[KG_ROWS], rd[KG_ROWS];
+        float2 pp[KG_ROWS];
+        unsigned int dk[KG_ROWS];
+#pragma unroll
+        for (int r = 0; r < KG_ROWS; ++r) {
+            const long long i = i0 + 32 * r + lane;
+            const bool in = i < w1;
+            sl[r] = in ? max(tiles[i], 0) : 0;
+            rd[r] = in ? radius[i] : 0;
+            pp[r] = in ? uv[i] : make_float2(0.f, 0.f);
+            dk[r] = in ? __float_as_uint(depth[i]) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < KG_ROWS; ++r) {
+            const long long i = i0 + 32 * r + lane;
+            int x0, y0, w;
+            const int n = keygen_count(sl[r], rd[r], pp[r], gx, gy, x0, y0, w);
+            const unsigned em = __ballot_sync(0xffffffffu, n > 0);
+            if (n > 0) {
+                const unsigned int o = pos + __popc(em & lt_mask);
+                dkeys[o] = dk[r];
+                dvals[o] = (int)i;
+                rect[i] = make_int4(x0, y0, w, n);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((dk[r] >> (8 * p)) & 255u)], 1u);
             }
-            zsum += (unsigned)(slots - n);  // never-written slots stay (0, 0): sort_gaussian.cu:98-99
-            if (n > 0) key = __float_as_uint(depth[i]);
-            dkeys[i] = key;
-            dvals[i] = (int)i;
-            cnt[i] = n;
-        }
-        // histograms: non-emitting Gaussians all carry digit 255 -> one aggregated add per warp
-        const unsigned ne = __ballot_sync(0xffffffffu, i < P && n == 0);
-        if (n > 0) {
-#pragma unroll
-            for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 255u)], 1u);
-        }
-        if (lane == 0 && ne) {
-            const unsigned c = __popc(ne);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + 255], c);
+            pos += __popc(em);
         }
     }
 #pragma unroll
@@ -232,23 +336,93 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, const float2* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// phase 2c: start offsets in depth order -- single-pass chained scan of n[order[i]] (+ Z)
+// ------------------------------------------------------------------------------------------------
+// One kernel instead of block sums + spine + apply: the 4-byte gathers rect[order[i]].n (one 32-byte
+// sector each) are done once.  Tiles of 2048 are taken by ticket; warp 0 resolves the tile's
+// exclusive prefix by decoupled look-back over one (flag | inclusive prefix) word per tile, 32
+// predecessors per round trip.
+__global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int* __restrict__ n_dev,
+                                                             const int4* __restrict__ rect,
+                                                             const int* __restrict__ order,
+                                                             const unsigned int* __restrict__ zcount,
+                                                             int* __restrict__ start,
+                                                             unsigned int* __restrict__ status,
+                                                             unsigned int* __restrict__ ticket) {
+    __shared__ int s_warp[SC_NT / 32 + 1];
+    __shared__ int s_tile;
+    __shared__ unsigned int s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int N = (int)*n_dev;
+    const long long base = (long long)tile * SC_TILE + (long long)threadIdx.x * SC_IPT;
+    if ((long long)tile * SC_TILE >= N) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int id[SC_IPT], v[SC_IPT];
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) id[k] = base + k < N ? order[base + k] : -1;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) {
+        v[k] = id[k] >= 0 ? rect[id[k]].w : 0;
+        sum += v[k];
+    }
+    int total;
+    const int excl = block_excl_scan<SC_NT>(sum, s_warp, total);
+    if (warp == 0) {
+        unsigned int pre = 0;
+        if (tile > 0) {
+            if (lane == 0) st_relaxed(status + tile, RS_FLAG_AGG | (unsigned)total);
+            int j = tile - 1;
+            while (true) {
+                const unsigned int w = (j - lane >= 0) ? ld_relaxed(status + (j - lane)) : RS_FLAG_PRE;
+                const unsigned ready = __ballot_sync(0xffffffffu, (w & ~RS_VALUE_MASK) != 0u);
+                const unsigned isp = __ballot_sync(0xffffffffu, (w & RS_FLAG_PRE) != 0u);
+                const int run = (~ready) ? __ffs(~ready) - 1 : 32;  // predecessors ready without a gap
+                const int fp = isp ? __ffs(isp) - 1 : 32;           // nearest one holding a full prefix
+                const int take = min(run, fp + 1);
+                unsigned int add = lane < take ? (w & RS_VALUE_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                pre += add;
+                if (fp < run) break;
+                j -= take;
+                if (take == 0) __nanosleep(20);
+            }
+        }
+        if (lane == 0) {
+            st_relaxed(status + tile, RS_FLAG_PRE | (pre + (unsigned)total));
+            s_prefix = pre;
+        }
+    }
+    __syncthreads();
+    int run = (int)(s_prefix + *zcount) + excl;
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) {
+        if (base + k < N) start[base + k] = run;
+        run += v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // phase 2d: duplication in depth order + histograms of the tile-digit passes
 // ------------------------------------------------------------------------------------------------
 constexpr int DUP_NT = 256;
 constexpr int DUP_SMALL = 8;
 
-__global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const int* __restrict__ order /*[P] depth order*/,
-                                                           const int* __restrict__ cnt,
-                                                           const int* __restrict__ start_sorted,
-                                                           const float2* __restrict__ uv,
-                                                           const int* __restrict__ radius, int gx, int gy,
-                                                           int npass, const unsigned int* __restrict__ zcount,
+__global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* __restrict__ pcount,
+                                                           const int* __restrict__ order /*[Pc] depth order*/,
+                                                           const int4* __restrict__ rect /*[P] {x0, y0, w, n}*/,
+                                                           const int* __restrict__ start_sorted, int gx, int npass,
+                                                           const unsigned int* __restrict__ zcount,
                                                            unsigned int* __restrict__ keys, int* __restrict__ vals,
                                                            unsigned int* __restrict__ hist /*[npass][256]*/) {
     __shared__ unsigned int s_hist[MAX_TPASS * 256];
     for (int i = threadIdx.x; i < npass * 256; i += DUP_NT) s_hist[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int P = (int)*pcount;  // emitting Gaussians (keygen_kernel)
     // phantom prefix: Z entries (tile 0, idx 0)
     const unsigned int Z = *zcount;
     for (long long e = (long long)blockIdx.x * DUP_NT + threadIdx.x; e < Z; e += (long long)gridDim.x * DUP_NT) {
@@ -263,15 +437,12 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const int* __r
         int n = 0, start = 0, x0 = 0, y0 = 0, w = 1, id = 0;
         if (i < P) {
             id = order[i];
-            n = cnt[id];
-            if (n > 0) {
-                start = start_sorted[i];
-                const float2 c = uv[id];
-                const Rect q = get_rect(c.x, c.y, radius[id], gx, gy);
-                x0 = q.x0;
-                y0 = q.y0;
-                w = max(q.x1 - q.x0, 1);
-            }
+            start = start_sorted[i];
+            const int4 r = rect[id];  // one 16-byte gather per Gaussian
+            x0 = r.x;
+            y0 = r.y;
+            w = r.z;
+            n = r.w;
         }
         // small footprints: each lane emits its own run
         if (n > 0 && n <= DUP_SMALL) {
@@ -320,57 +491,76 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(int P, const int* __r
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_NT = 256;
 constexpr int RS_WARPS = RS_NT / 32;
-constexpr int RS_IPT = 16;
-constexpr int RS_TILE = RS_NT * RS_IPT;  // 4096 keys per CTA
-constexpr unsigned int RS_FLAG_AGG = 1u << 30;
-constexpr unsigned int RS_FLAG_PRE = 2u << 30;
-constexpr unsigned int RS_VALUE_MASK = (1u << 30) - 1u;
-constexpr int RS_LB = 8;  // look-back window per round trip
+constexpr int RS_IPT = 16;               // keys per thread of the tile passes (4096 keys per CTA)
+constexpr int RS_TILE = RS_NT * RS_IPT;
 
+template <int IPT>
 struct RsSmem {
-    unsigned int keys[RS_TILE];          // 16 KB exchange buffer
-    int vals[RS_TILE];                   // 16 KB
+    unsigned int keys[RS_NT * IPT];      // 16 KB exchange buffer (IPT = 16)
+    int vals[RS_NT * IPT];               // 16 KB
     unsigned int whist[RS_WARPS][256];   //  8 KB per-warp digit counts -> per-warp offsets
     int gadj[256];                       // global base of the digit minus its tile-local start
     int scan_tmp[RS_NT / 32 + 1];
     int tile_id;
 };
 
-__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// m &= (lanes whose digit agrees with mine in bit B): LOP3 -> predicate, VOTE, SEL, LOP3 m & (bal ^ y)
+template <int B>
+__device__ __forceinline__ void peer_bit(unsigned d, unsigned& m) {
+    unsigned bal, y;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "selp.b32 %1, 0, -1, p;\n\t}"
+        : "=r"(bal), "=r"(y)
+        : "r"(d), "n"(1u << B));
+    asm("lop3.b32 %0, %0, %1, %2, 0x60;" : "+r"(m) : "r"(bal), "r"(y));
 }
 
-__global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, const unsigned int* __restrict__ kin,
+// DEVN: the element count is read from *n_dev (compacted Gaussians; the grid is sized for an upper
+// bound).  LB: predecessors inspected per look-back round trip.  When all tiles of a pass are
+// resident at once (the L2-resident depth passes: <= one wave) every tile publishes its aggregate
+// at about the same time and the full prefixes then advance LB tiles per round trip while each
+// waiting tile walks back LB per round trip: tile k resolves after ~k / (2 LB) round trips, so
+// those passes want a wide window; the multi-wave tile passes resolve within the first window.
+// IPT: keys per thread (16).  A/B on BASELINE config #3 (profiles/r1_ab_sort.md): 8 keys per thread
+// at 6 CTAs/SM and look-back windows of 16 / 32 were not faster for the L2-resident depth passes;
+// what helped them was the single-lane wait below (gate_ns).
+template <bool DEVN, int LB, int NB, int IPT>
+__global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int N, const unsigned int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ kin,
                                                             const int* __restrict__ vin,
                                                             unsigned int* __restrict__ kout, int* __restrict__ vout,
                                                             const unsigned int* __restrict__ hist /*[256] this pass*/,
                                                             unsigned int* __restrict__ status /*[ntiles][256]*/,
-                                                            unsigned int* __restrict__ ticket) {
+                                                            unsigned int* __restrict__ ticket, int gate_ns) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
-    RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
+    RsSmem<IPT>& sm = *reinterpret_cast<RsSmem<IPT>*>(rs_raw);
+    constexpr int TILE = RS_NT * IPT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) sm.tile_id = (int)atomicAdd(ticket, 1u);  // tiles are ordered by start time
 #pragma unroll
     for (int k = 0; k < 256 / 32; ++k) sm.whist[warp][lane + 32 * k] = 0;
+    if (DEVN) N = (int)*n_dev;
     __syncthreads();
     const int tile = sm.tile_id;
-    const long long tile_base = (long long)tile * RS_TILE;
-    const int valid = (int)min((long long)RS_TILE, (long long)N - tile_base);
+    const long long tile_base = (long long)tile * TILE;
+    const int valid = (int)min((long long)TILE, (long long)N - tile_base);
+    if (DEVN && valid <= 0) return;  // the grid is sized for the host-side upper bound of N
 
     // ---- load (warp-striped: element order = warp, item, lane) --------------------------------
-    unsigned int key[RS_IPT];
-    unsigned short rank[RS_IPT];
-    const int wbase = warp * (32 * RS_IPT);
+    unsigned int key[IPT];
+    unsigned short rank[IPT];
+    const int wbase = warp * (32 * IPT);
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         const int e = wbase + i * 32 + lane;
-        key[i] = e < valid ? kin[tile_base + e] : 0xffffffffu;  // padding sorts last: digit 255 in every pass
+        // kept ROTATED so that this pass's digit sits in the low byte (bit tests and digit extraction
+        // need no shift); rotated back on the way out.  Padding sorts last: digit 255 in every pass.
+        const unsigned int k = e < valid ? kin[tile_base + e] : 0xffffffffu;
+        key[i] = __funnelshift_r(k, k, shift);
     }
 
     // ---- rank inside the warp with match.any (warp-ballot ranking) ------------------------------
@@ -380,22 +570,27 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
     // The peer mask (lanes holding the same digit) is built from 8 ballots, one per digit bit:
     // match.any.sync costs time proportional to the number of DISTINCT values in the warp (measured:
     // a pass over uniformly distributed digits ran 1.7x slower than one over 4 distinct digits).
-    unsigned peers[RS_IPT];
+    unsigned peers[IPT];
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        const unsigned d = key[i] >> shift;
+    for (int i = 0; i < IPT; ++i) {
+        const unsigned d = key[i];
         unsigned m = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
+        // digit bits >= NB are zero in every real key of this pass (top tile-id digit; the host passes
+        // one bit more than the keys need, so that the 0xFFFFFFFF padding of the last tile never
+        // matches a real key)
+        peer_bit<0>(d, m);
+        if constexpr (NB > 1) peer_bit<1>(d, m);
+        if constexpr (NB > 2) peer_bit<2>(d, m);
+        if constexpr (NB > 3) peer_bit<3>(d, m);
+        if constexpr (NB > 4) peer_bit<4>(d, m);
+        if constexpr (NB > 5) peer_bit<5>(d, m);
+        if constexpr (NB > 6) peer_bit<6>(d, m);
+        if constexpr (NB > 7) peer_bit<7>(d, m);
         peers[i] = m;
     }
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        const unsigned d = (key[i] >> shift) & 255u;
+    for (int i = 0; i < IPT; ++i) {
+        const unsigned d = key[i] & 255u;
         const int leader = __ffs(peers[i]) - 1;
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(&sm.whist[warp][d], (unsigned)__popc(peers[i]));
@@ -404,9 +599,9 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
         rank[i] = (unsigned short)(base + __popc(peers[i] & lt_mask));
     }
     // payload: fetched now (the match masks are dead), lands while the digit offsets are resolved
-    int val[RS_IPT];
+    int val[IPT];
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         const int e = wbase + i * 32 + lane;
         val[i] = e < valid ? vin[tile_base + e] : 0;
     }
@@ -420,7 +615,7 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
         sm.whist[w][tid] = count;
         count += c;
     }
-    if (tid == 255) count -= (unsigned)(RS_TILE - valid);  // padding keys are not real
+    if (tid == 255) count -= (unsigned)(TILE - valid);  // padding keys are not real
     unsigned int* my_status = status + (size_t)tile * 256 + tid;
     if (tile != 0) st_relaxed(my_status, RS_FLAG_AGG | count);  // as early as possible: successors sum it
 
@@ -434,18 +629,18 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
         excl = (unsigned)block_excl_scan<RS_NT>((int)hist[tid], sm.scan_tmp, tot);
         st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
     } else {
-        // decoupled look-back, RS_LB predecessors per round trip (independent loads in flight);
+        // decoupled look-back, LB predecessors per round trip (independent loads in flight);
         // a serial walk costs one L2 latency per predecessor and dominated the pass
         int j = tile - 1;
         while (true) {
-            unsigned int v[RS_LB];
+            unsigned int v[LB];
 #pragma unroll
-            for (int k = 0; k < RS_LB; ++k)
+            for (int k = 0; k < LB; ++k)
                 v[k] = (j - k >= 0) ? ld_relaxed(status + (size_t)(j - k) * 256 + tid) : RS_FLAG_PRE;
             int used = 0;
             bool done = false;
 #pragma unroll
-            for (int k = 0; k < RS_LB; ++k) {
+            for (int k = 0; k < LB; ++k) {
                 if (!done && used == k && (v[k] & ~RS_VALUE_MASK) != 0u) {
                     excl += v[k] & RS_VALUE_MASK;
                     used = k + 1;
@@ -454,7 +649,17 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
             }
             if (done) break;
             j -= used;
-            if (used == 0) __nanosleep(20);
+            if (gate_ns > 0) {
+                // nothing published by tile j yet: ONE lane per warp waits for it (a tile's 256 words are
+                // written together), so waiting warps do not take issue slots from the tiles still ranking
+                if (__all_sync(0xffffffffu, used == 0)) {
+                    if (lane == 0)
+                        while ((ld_relaxed(status + (size_t)j * 256 + tid) & ~RS_VALUE_MASK) == 0u) __nanosleep(gate_ns);
+                    __syncwarp();
+                }
+            } else if (used == 0) {
+                __nanosleep(20);
+            }
         }
         st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
     }
@@ -465,8 +670,8 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
 
     // ---- exchange through shared memory (tile-local sorted order) ------------------------------
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        const unsigned d = (key[i] >> shift) & 255u;
+    for (int i = 0; i < IPT; ++i) {
+        const unsigned d = key[i] & 255u;
         const unsigned pos = sm.whist[warp][d] + rank[i];
         sm.keys[pos] = key[i];
         sm.vals[pos] = val[i];
@@ -476,10 +681,10 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
     // ---- coalesced scatter ----------------------------------------------------------------------
 #pragma unroll 4
     for (int j = tid; j < valid; j += RS_NT) {
-        const unsigned int k = sm.keys[j];
-        const unsigned d = (k >> shift) & 255u;
+        const unsigned int k = sm.keys[j];  // rotated key
+        const unsigned d = k & 255u;
         const long long g = (long long)sm.gadj[d] + j;
-        kout[g] = k;
+        kout[g] = __funnelshift_l(k, k, shift);
         vout[g] = sm.vals[j];
     }
 }
@@ -489,32 +694,49 @@ __global__ void __launch_bounds__(RS_NT, 4) onesweep_kernel(int N, int shift, co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_range_kernel(int M, const unsigned int* __restrict__ keys,
                                                          int2* __restrict__ tile_range, int T) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    const unsigned int cur = keys[i];
-    if (cur >= (unsigned)T) return;  // cannot happen for keys produced by duplicate_kernel
-    if (i == 0) tile_range[cur].x = 0;
-    if (i == M - 1) tile_range[cur].y = M;
-    if (i == 0) return;
-    const unsigned int prev = keys[i - 1];
-    if (prev != cur) {
-        if (prev < (unsigned)T) tile_range[prev].y = (int)i;
-        tile_range[cur].x = (int)i;
+    // four keys per thread: one 16-byte load + the left neighbour
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= M) return;
+    unsigned int k[4];
+    if (i0 + 3 < M) {
+        const uint4 v = *reinterpret_cast<const uint4*>(keys + i0);
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) k[e] = i0 + e < M ? keys[i0 + e] : 0u;
+    }
+    unsigned int prev = i0 > 0 ? keys[i0 - 1] : 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const long long i = i0 + e;
+        if (i >= M) break;
+        const unsigned int cur = k[e];
+        if (cur < (unsigned)T) {  // always true for keys produced by duplicate_kernel
+            if (i == 0) tile_range[cur].x = 0;
+            if (i == M - 1) tile_range[cur].y = M;
+            if (i > 0 && prev != cur) {
+                if (prev < (unsigned)T) tile_range[prev].y = (int)i;
+                tile_range[cur].x = (int)i;
+            }
+        }
+        prev = cur;
     }
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// digit passes over the tile id
-static int tile_passes(int T) {
+// significant bits of the tile ids 0..T-1, and the digit passes over them
+static int tile_bits(int T) {
     int bits = 0;
-    while (bits < 31 && (1ll << bits) < (long long)T) ++bits;  // bits needed for tile ids 0..T-1
-    return (bits + 7) / 8;
+    while (bits < 31 && (1ll << bits) < (long long)T) ++bits;
+    return bits;
 }
+static int tile_passes(int T) { return (tile_bits(T) + 7) / 8; }
 
 struct SortLayout {
-    size_t dkeys[2], dvals[2], cnt, start, tkeys[2], tvals, bsum, zero0, hist, ticket, zcount, status_d, status_t, total;
-    int tpass, ntiles_d, ntiles_t, nb_scan;
+    size_t dkeys[2], dvals[2], rect, start, tkeys[2], tvals, zero0, hist, ticket, zcount, pcount, status_k, status_s, status_d, status_t,
+        total;
+    int tpass, ntiles_d, ntiles_t, nb_scan, nchunks_k;
 };
 
 static SortLayout sort_layout(int P, long long M, int T) {
@@ -523,6 +745,7 @@ static SortLayout sort_layout(int P, long long M, int T) {
     L.ntiles_d = (int)(((long long)P + RS_TILE - 1) / RS_TILE);
     L.ntiles_t = (int)((M + RS_TILE - 1) / RS_TILE);
     L.nb_scan = (int)(((long long)P + SC_TILE - 1) / SC_TILE);
+    L.nchunks_k = (int)(((long long)P + 255) / 256) + 1;  // >= keygen grid (<= ceil(P / 256) CTAs)
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t o = off;
@@ -531,16 +754,18 @@ static SortLayout sort_layout(int P, long long M, int T) {
     };
     for (int k = 0; k < 2; ++k) L.dkeys[k] = take((size_t)P * 4);
     for (int k = 0; k < 2; ++k) L.dvals[k] = take((size_t)P * 4);
-    L.cnt = take((size_t)P * 4);
+    L.rect = take((size_t)P * 16);
     L.start = take((size_t)P * 4);
     for (int k = 0; k < 2; ++k) L.tkeys[k] = take((size_t)M * 4);
     L.tvals = take((size_t)M * 4);
-    L.bsum = take((size_t)(L.nb_scan + 2) * 8);
     // zero-initialised region: hist | ticket | zcount | status
     L.zero0 = off;
     L.hist = take((size_t)(4 + MAX_TPASS) * 256 * 4);
-    L.ticket = take((size_t)(4 + MAX_TPASS) * 4);
+    L.ticket = take((size_t)(4 + MAX_TPASS + 2) * 4);  // one per onesweep pass + keygen + offset scan
     L.zcount = take(4);
+    L.pcount = take(4);
+    L.status_k = take((size_t)L.nchunks_k * 4);
+    L.status_s = take((size_t)(L.nb_scan + 1) * 4);
     L.status_d = take((size_t)4 * L.ntiles_d * 256 * 4);
     L.status_t = take((size_t)L.tpass * L.ntiles_t * 256 * 4);
     L.total = off;
@@ -576,9 +801,9 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
     const int nb = (P + SC_TILE - 1) / SC_TILE;
     long long* bsum = reinterpret_cast<long long*>(ws);
     long long* total_dev = bsum + nb;
-    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, nullptr, bsum);
+    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
     scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
-    if (offsets) scan_apply_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, nullptr, bsum, nullptr, offsets);
+    if (offsets) scan_apply_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, bsum, offsets);
     int rc = check_launch("sort_scan");
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
@@ -624,31 +849,45 @@ int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     e = cudaMemsetAsync(base + L.zero0, 0, L.total - L.zero0, st);
     if (e != cudaSuccess) return set_error((int)e, "sort_gaussian: memset workspace failed");
     const int sms = sm_count > 0 ? sm_count : 148;
-    const long long nchunks = ((long long)P + KG_NT - 1) / KG_NT;
-    const unsigned sgrid = (unsigned)min(nchunks, (long long)sms * 8);
+    unsigned int* pcount = U32(L.pcount);
 
-    // 2a: depth keys
-    keygen_kernel<<<sgrid, KG_NT, 0, st>>>(P, reinterpret_cast<const float2*>(uv), depth, radius, tiles, gx, gy,
-                                           U32(L.dkeys[0]), I32(L.dvals[0]), I32(L.cnt), hist, zcount);
+    // 2a: depth keys of the emitting Gaussians, compacted in index order; *pcount = Pc.  At most one
+    // wave of CTAs (4 per SM); each warp owns `seg` consecutive Gaussians.
+    const long long warps_needed = ((long long)P + 31) / 32;
+    const unsigned kgrid = (unsigned)max(1ll, min((warps_needed + KG_WARPS - 1) / KG_WARPS, (long long)sms * 4));
+    const long long per_warp = ((long long)P + (long long)kgrid * KG_WARPS - 1) / ((long long)kgrid * KG_WARPS);
+    const int seg = (int)((per_warp + 31) / 32 * 32);
+    if ((size_t)kgrid > (size_t)L.nchunks_k) return set_error(MSB_ERR_WORKSPACE, "sort_gaussian: keygen status");
+    keygen_kernel<<<kgrid, KG_NT, 0, st>>>(P, seg, reinterpret_cast<const float2*>(uv), depth, radius, tiles, gx, gy,
+                                           U32(L.dkeys[0]), I32(L.dvals[0]), reinterpret_cast<int4*>(base + L.rect), hist,
+                                           zcount,
+                                           U32(L.status_k), ticket + 4 + MAX_TPASS, pcount);
     int rc = check_launch("sort_gaussian/keygen");
     if (rc) return rc;
 
-    static_assert(sizeof(RsSmem) <= 48 * 1024, "onesweep shared memory");
-    // 2b: four depth-digit passes over the Gaussians (ends in buffer 0)
+    static_assert(sizeof(RsSmem<RS_IPT>) <= 48 * 1024, "onesweep shared memory");
+    // 2b: four depth-digit passes over the Pc emitting Gaussians (ends in buffer 0).  Grids are sized
+    // for the host-side bound min(P, M) >= Pc; surplus CTAs exit after taking their ticket.
+    const long long pc_max = min((long long)P, M);
+    const int nb_scan = (int)((pc_max + SC_TILE - 1) / SC_TILE);
+    const int ntiles_d = (int)((pc_max + RS_TILE - 1) / RS_TILE);
+    static const int gate_ns = [] { const char* e = getenv("MSB_SORT_GATE"); return e ? atoi(e) : 100; }();
     for (int p = 0; p < 4; ++p) {
-        onesweep_kernel<<<L.ntiles_d, RS_NT, sizeof(RsSmem), st>>>(
-            P, 8 * p, U32(L.dkeys[p % 2]), I32(L.dvals[p % 2]), U32(L.dkeys[(p + 1) % 2]), I32(L.dvals[(p + 1) % 2]),
-            hist + p * 256, U32(L.status_d) + (size_t)p * L.ntiles_d * 256, ticket + p);
+        unsigned int* kin = U32(L.dkeys[p % 2]);
+        int* vin = I32(L.dvals[p % 2]);
+        unsigned int* kout = U32(L.dkeys[(p + 1) % 2]);
+        int* vout = I32(L.dvals[(p + 1) % 2]);
+        unsigned int* stat = U32(L.status_d) + (size_t)p * L.ntiles_d * 256;
+        onesweep_kernel<true, 8, 8, RS_IPT><<<ntiles_d, RS_NT, sizeof(RsSmem<RS_IPT>), st>>>(
+            P, pcount, 8 * p, kin, vin, kout, vout, hist + p * 256, stat, ticket + p, gate_ns);
         rc = check_launch("sort_gaussian/onesweep(depth)");
         if (rc) return rc;
     }
     const int* order = I32(L.dvals[0]);
 
     // 2c: start offsets in depth order (exclusive scan of the emitted counts, + Z)
-    long long* bsum = reinterpret_cast<long long*>(base + L.bsum);
-    scan_block_sums_kernel<<<L.nb_scan, SC_NT, 0, st>>>(P, I32(L.cnt), order, bsum);
-    scan_spine_kernel<<<1, 1024, 0, st>>>(L.nb_scan, bsum, bsum + L.nb_scan);
-    scan_apply_kernel<true><<<L.nb_scan, SC_NT, 0, st>>>(P, I32(L.cnt), order, bsum, zcount, I32(L.start));
+    scan_offsets_kernel<<<nb_scan, SC_NT, 0, st>>>(pcount, reinterpret_cast<const int4*>(base + L.rect), order, zcount,
+                                                   I32(L.start), U32(L.status_s), ticket + 4 + MAX_TPASS + 1);
     rc = check_launch("sort_gaussian/offsets");
     if (rc) return rc;
 
@@ -658,20 +897,41 @@ int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     tv[L.tpass % 2] = idx_sorted;
     tv[(L.tpass + 1) % 2] = I32(L.tvals);
     unsigned int* thist = hist + 4 * 256;
-    duplicate_kernel<<<sgrid, DUP_NT, 0, st>>>(P, order, I32(L.cnt), I32(L.start), reinterpret_cast<const float2*>(uv),
-                                               radius, gx, gy, L.tpass, zcount, tk[0], tv[0], thist);
+    const unsigned dgrid = (unsigned)max(1ll, min((pc_max + DUP_NT - 1) / DUP_NT, (long long)sms * 8));
+    duplicate_kernel<<<dgrid, DUP_NT, 0, st>>>(pcount, order, reinterpret_cast<const int4*>(base + L.rect), I32(L.start),
+                                               gx, L.tpass, zcount, tk[0], tv[0], thist);
     rc = check_launch("sort_gaussian/duplicate");
     if (rc) return rc;
 
     // 2e: tile-digit passes over the duplicates
+    const int tbits = tile_bits(T);
     for (int p = 0; p < L.tpass; ++p) {
-        onesweep_kernel<<<L.ntiles_t, RS_NT, sizeof(RsSmem), st>>>(
-            (int)M, 8 * p, tk[p % 2], tv[p % 2], tk[(p + 1) % 2], tv[(p + 1) % 2], thist + p * 256,
-            U32(L.status_t) + (size_t)p * L.ntiles_t * 256, ticket + 4 + p);
+        // digit bits the ranking compares: those the tile ids use in this digit, plus one (see the kernel)
+        const int nb = min(8, max(1, tbits - 8 * p) + 1);
+        const unsigned int* kin = tk[p % 2];
+        const int* vin = tv[p % 2];
+        unsigned int* kout = tk[(p + 1) % 2];
+        int* vout = tv[(p + 1) % 2];
+        const unsigned int* h = thist + p * 256;
+        unsigned int* stat = U32(L.status_t) + (size_t)p * L.ntiles_t * 256;
+        unsigned int* tick = ticket + 4 + p;
+#define MSB_TILE_PASS(NB_) \
+    onesweep_kernel<false, 8, NB_, RS_IPT><<<L.ntiles_t, RS_NT, sizeof(RsSmem<RS_IPT>), st>>>((int)M, nullptr, 8 * p, kin, vin, kout, \
+                                                                             vout, h, stat, tick, gate_ns)
+        switch (nb) {
+            case 2: MSB_TILE_PASS(2); break;
+            case 3: MSB_TILE_PASS(3); break;
+            case 4: MSB_TILE_PASS(4); break;
+            case 5: MSB_TILE_PASS(5); break;
+            case 6: MSB_TILE_PASS(6); break;
+            case 7: MSB_TILE_PASS(7); break;
+            default: MSB_TILE_PASS(8); break;
+        }
+#undef MSB_TILE_PASS
         rc = check_launch("sort_gaussian/onesweep(tile)");
         if (rc) return rc;
     }
-    tile_range_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((int)M, tk[L.tpass % 2],
+    tile_range_kernel<<<(unsigned)((M + 1023) / 1024), 256, 0, st>>>((int)M, tk[L.tpass % 2],
                                                                   reinterpret_cast<int2*>(tile_range), T);
     return check_launch("sort_gaussian/tile_range");
 }
