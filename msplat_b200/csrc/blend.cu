@@ -440,12 +440,6 @@ __global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v2(const float4* __res
 constexpr int BW_GQ = 16;  // Gaussians per phase-2 group
 constexpr int BW_PS = 33;  // row stride of the (X, w) matrix in float2: conflict-free LDS.64 in both phases
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
 
 template <int CH, int B>
 struct Bwd3 {

@@ -116,12 +116,31 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
     const Cam c = load_cam(intr, extr);
     const CamCenter cc = cam_center(c);
-    if (tid == 0) s_cnt = 0;
-    slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
-    slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
-    slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
-    slab_load<RP_NT>(s_op, opacity, g0, rows);
+    // full blocks: the four input slabs arrive as TMA bulk copies issued by one thread (3 + 3 + 4 + 1 KB
+    // at G = 256), everyone waits on the mbarrier; the ragged last block uses the per-thread path
+    __shared__ unsigned long long s_bar;
+    const bool full = rows == G;
+    if (tid == 0) {
+        s_cnt = 0;
+        if (full) mbar_init(&s_bar, 1);
+    }
     __syncthreads();
+    if (full) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)(11 * G * sizeof(float)));
+            bulk_g2s(s_xyz, xyz + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_scale, scale + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_quat, quat + g0 * 4, 4 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_op, opacity + g0, G * sizeof(float), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+        slab_load<RP_NT>(s_op, opacity, g0, rows);
+        __syncthreads();
+    }
 
     // ---- phase 1: geometry + basis, one thread per Gaussian -------------------------------------
     const int t = tid;
@@ -216,10 +235,22 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
             }
         }
     }
-    __syncthreads();
-    slab_store<RP_NT>(rec, sm, g0 * 8, rows * 8);
-    slab_store<RP_NT>(uv, s_uv, g0 * 2, rows * 2);
-    slab_store<RP_NT>(featp, s_feat, g0 * Cpad, rows * Cpad);
+    if (full) {
+        fence_async_smem();  // this thread's slab writes -> visible to the bulk stores below
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(rec + g0 * 8, sm, 8 * G * sizeof(float));
+            bulk_s2g(uv + g0 * 2, s_uv, 2 * G * sizeof(float));
+            bulk_s2g(featp + g0 * Cpad, s_feat, (unsigned)((size_t)Cpad * G * sizeof(float)));
+            bulk_commit();
+            bulk_wait_read();  // shared memory must stay valid until the copy engine has read it
+        }
+    } else {
+        __syncthreads();
+        slab_store<RP_NT>(rec, sm, g0 * 8, rows * 8);
+        slab_store<RP_NT>(uv, s_uv, g0 * 2, rows * 2);
+        slab_store<RP_NT>(featp, s_feat, g0 * Cpad, rows * Cpad);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,13 +293,31 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     const int rows = (int)min((long long)G, (long long)P - g0);
     const Cam c = load_cam(intr, extr);
     const CamCenter cc = cam_center(c);
-    if (tid == 0) s_cnt = 0;
-    slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
-    slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
-    slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
-    slab_load<RP_NT>(s_grec, grec, g0 * 8, rows * 8);
-    slab_load<RP_NT>(s_gfeat, gfeat, g0 * Cpad, rows * Cpad);
+    __shared__ unsigned long long s_bar;
+    const bool full = rows == G;  // full blocks move their slabs with TMA bulk copies (see the forward kernel)
+    if (tid == 0) {
+        s_cnt = 0;
+        if (full) mbar_init(&s_bar, 1);
+    }
     __syncthreads();
+    if (full) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)((18 + (size_t)Cpad) * G * sizeof(float)));
+            bulk_g2s(s_xyz, xyz + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_scale, scale + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_quat, quat + g0 * 4, 4 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_grec, grec + g0 * 8, 8 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_gfeat, gfeat + g0 * Cpad, (unsigned)((size_t)Cpad * G * sizeof(float)), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+        slab_load<RP_NT>(s_grec, grec, g0 * 8, rows * 8);
+        slab_load<RP_NT>(s_gfeat, gfeat, g0 * Cpad, rows * Cpad);
+        __syncthreads();
+    }
 
     // ---- phase 1: basis of the Gaussians that received a colour gradient -------------------------
     const int t = tid;
@@ -358,18 +407,15 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
                                                b[it * WD + (WD > 2 ? 2 : 0)] * dv, b[it * WD + (WD > 3 ? 3 : 0)] * dv);
                         float4* q = reinterpret_cast<float4*>(op) + un;
                         if (accumulate) {
-                            if (dv != 0.f) {
-                                const float4 old = *q;
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                                *q = o;
-                            }
+                            // fire-and-forget vector reduction: no read of the old row, no load latency
+                            if (dv != 0.f) red_add_v4(reinterpret_cast<float*>(q), o.x, o.y, o.z, o.w);
                         } else {
                             *q = o;
                         }
                     } else {
                         const float o = b[it * WD] * dv;
                         if (accumulate) {
-                            if (dv != 0.f) op[un] += o;
+                            if (dv != 0.f) atomicAdd(op + un, o);  // result unused -> RED
                         } else {
                             op[un] = o;
                         }
@@ -434,22 +480,42 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
         s_scale[3 * t + 2] = ds[2];
         reinterpret_cast<float4*>(s_quat)[t] = make_float4(dq[0], dq[1], dq[2], dq[3]);
         if (accumulate) {
-            if (dop != 0.f) dL_dopacity[g0 + t] += dop;
+            if (dop != 0.f) atomicAdd(dL_dopacity + g0 + t, dop);  // result unused -> RED
         } else {
             dL_dopacity[g0 + t] = dop;
         }
     }
-    __syncthreads();
-    if (accumulate) {
-        slab_store_acc<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
-        slab_store_acc<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
-        slab_store_acc<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+    if (full) {
+        // gradient slabs leave as bulk stores, or as bulk FP32 reduce-adds when accumulating over views
+        // (cp.reduce.async.bulk: the read-modify-write happens at the L2, not in this SM)
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (accumulate) {
+                bulk_s2g_add_f32(dL_dxyz + g0 * 3, s_xyz, 3 * G * sizeof(float));
+                bulk_s2g_add_f32(dL_dscale + g0 * 3, s_scale, 3 * G * sizeof(float));
+                bulk_s2g_add_f32(dL_dquat + g0 * 4, s_quat, 4 * G * sizeof(float));
+            } else {
+                bulk_s2g(dL_dxyz + g0 * 3, s_xyz, 3 * G * sizeof(float));
+                bulk_s2g(dL_dscale + g0 * 3, s_scale, 3 * G * sizeof(float));
+                bulk_s2g(dL_dquat + g0 * 4, s_quat, 4 * G * sizeof(float));
+            }
+            bulk_commit();
+        }
     } else {
-        slab_store<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
-        slab_store<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
-        slab_store<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+        __syncthreads();
+        if (accumulate) {
+            slab_store_acc<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+            slab_store_acc<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+            slab_store_acc<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+        } else {
+            slab_store<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+            slab_store<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+            slab_store<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+        }
     }
     if (CAM) cam_reduce_atomic<RP_NT>(cam, dL_dintr, dL_dextr, s_red);
+    if (full && tid == 0) bulk_wait_read();  // shared memory stays valid until the copy engine has read it
 }
 
 static size_t rp_smem_fwd(int deg, int Cpad) {
