@@ -140,15 +140,18 @@ def measured_peaks():
 
 
 # algorithmic HBM bytes per unit of each C-ABI call at SH3 RGB + depth (DESIGN.md "Kernels")
-def algorithmic_bytes(name, P, M, Cs, D, C, nvis=None, views=1):
+def algorithmic_bytes(name, P, M, Cs, D, C, nvis=None, views=1, nlive=None):
     nvis = P if nvis is None else nvis
+    nlive = nvis if nlive is None else nlive  # Gaussians that received a colour gradient (<= nvis)
     sh = 4 * Cs * D
     # backward: the first view of a step writes every output, the others accumulate (read + write)
     acc = (views - 1) / max(views, 1)
     T = {
         "render_preprocess_forward": P * (44 + 32 + 16 + 8 + 12) + nvis * sh,
-        "render_preprocess_backward": P * (40 + 32 + 16 + 4) + nvis * sh + P * 44 * (1 + acc)
-                                      + (1 - acc) * P * sh + acc * nvis * 2 * sh,
+        # inputs + packed grads + tiles; SH rows of the live Gaussians; 44 B of geometry grads (RMW when
+        # accumulating); dL_dshs: every row written by the first view, live rows read + written by the others
+        "render_preprocess_backward": P * (40 + 32 + 16 + 4) + nlive * sh + P * 44 * (1 + acc)
+                                      + (1 - acc) * P * sh + acc * nlive * 2 * sh,
         "project_point_forward": P * (12 + 12),
         "project_point_backward": P * (12 + 4 + 12 + 12),
         "compute_cov3d_forward": P * (12 + 16 + 1 + 24),
@@ -344,10 +347,15 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
         ids, tr = api.sort_gaussian(uv, depth, W, H, radius, tiles)
         from msplat_b200.alpha_blending import _blend_forward
         feat = torch.rand(P, C, device=xyz.device)
-        _, _, ncontrib, _ = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
+        _, final_T, ncontrib, packed = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
         pairs = int(ncontrib.sum())
         M = int(ids.numel())
         nvis = int((tiles > 0).sum())
+        # Gaussians that receive a colour gradient (blend at least one pixel): the only SH rows the backward touches
+        from msplat_b200.alpha_blending import _blend_backward
+        dfeat = _blend_backward(feat, ids, tr, 0.0, W, H, final_T, ncontrib, G[:C].contiguous(), packed)[3]
+        nlive = int((dfeat[:, :Cs] != 0).any(dim=1).sum())
+        del dfeat, packed
     hbm, sm_max, src = measured_peaks()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     f_hz = (clocks["sm_mhz"] if clocks else sm_max) * 1e6
@@ -357,7 +365,7 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
     for name, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         ms = tot / n
         st = {"ms": round(ms, 4), "share": round(tot / total_ms, 4), "calls": n}
-        ab = algorithmic_bytes(name, P, M, Cs, D, C, nvis, views)
+        ab = algorithmic_bytes(name, P, M, Cs, D, C, nvis, views, nlive)
         if ab is not None:
             st["GBps"] = round(ab / (ms * 1e-3) / 1e9, 1)
             st["hbm_frac"] = round(st["GBps"] / hbm, 3)
@@ -400,7 +408,7 @@ def stage_report(timing, args, api, params, cam, G, clocks, views):
         s["Gkeys_per_s"] = round(M / (s["ms"] * 1e-3) / 1e9, 3)
         s["note"] = f"M = {M} keys, 6 onesweep passes over 45 significant bits, 172 B/key algorithmic; peak {hbm} GB/s {src}"
     return {"roofline": roof, "stages": stages, "pairs_per_render": pairs, "keys_per_render": M,
-            "gaussians_touching_a_tile": nvis}
+            "gaussians_touching_a_tile": nvis, "gaussians_with_colour_gradient": nlive}
 
 
 # ------------------------------------------------------------------------------------------------

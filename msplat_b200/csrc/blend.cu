@@ -18,9 +18,10 @@
 //    per-pair work drops by ~3-4x without changing any pixel's result;
 //  * warp-vote early termination (a warp stops when its 32 pixels are done, the CTA when all are);
 //  * features live in shared memory (the reference re-reads them from global per pair);
-//  * backward: per-Gaussian gradients are reduced across the warp with a transposing butterfly
-//    (12 shuffles for 10 values instead of 50) and leave the SM as ONE red.global per value per
-//    warp, into a packed 32-byte gradient record; the reference issues (6+C) atomics per lane;
+//  * backward: every pair parks two scalars (X, w) in shared memory; a Gaussian-parallel phase turns
+//    them into the gradient moments in registers and leaves the SM as three vector reductions
+//    (red.global.add.v4/.v2) per Gaussian and warp, into a packed 32-byte gradient record; the
+//    reference issues (6+C) atomics per lane;
 //  * the backward walks only list positions below the tile's max ncontrib.
 #include <stdlib.h>
 
@@ -207,220 +208,7 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, v2 (kept behind MSB_BWD_V2=1 for A/B runs; the default is blend_bwd_kernel below)
-// ------------------------------------------------------------------------------------------------
-// Per warp-visit every lane produces NV = 6 + CH gradient contributions.  v2 parks them
-// in a per-warp shared-memory buffer [K visits][NV values][32 lanes] (row stride 36 floats:
-// conflict-free for the column writes and for the 16-byte row reads) and, every K visits, lane r
-// sums row r with 8 LDS.128 and issues one red.global: ~25 issue slots per visit.  The pair body
-// is branch-free: a failing pair runs with alpha = G = 0, which makes all of its contributions
-// exact zeros and leaves the replay state (T, suffix colour S) untouched.  The suffix colour is
-// carried as S_k = sum_{j>i} f_jk alpha_j T_j (identical algebra to the reference's accum_rec
-// recurrence, alpha_blending.cu:205-229: T_i (f - accum_rec) = f T_i - S / (1 - alpha_i)).
-template <int CH, int KV>
-struct BwdRed {
-    static constexpr int NV = 6 + CH;
-    static constexpr int K = KV;  // visits per flush, K * NV <= 32: CH=4 -> 3 (or 2), CH=8 -> 2, CH=16 -> 1
-    static constexpr int STRIDE = 36;
-    static constexpr int FLOATS = K * NV * STRIDE;  // per warp
-};
-
-template <int CH, int KV>
-__global__ void __launch_bounds__(BL_NT) blend_bwd_kernel_v2(const float4* __restrict__ rec,
-                                                          const float* __restrict__ featp, int fstride, int foff,
-                                                          const int* __restrict__ ids,
-                                                          const int2* __restrict__ tile_range, float bg,
-                                                          int c_valid, int W, int H,
-                                                          const float* __restrict__ final_T,
-                                                          const int* __restrict__ ncontrib,
-                                                          const float* __restrict__ dL_dimage,
-                                                          float* __restrict__ grec, float* __restrict__ gfeat,
-                                                          int geom_grads) {
-    using R = BwdRed<CH, KV>;
-    static_assert(R::K * R::NV <= 32 && R::K <= 4, "reduction rows must fit one warp");
-    constexpr int NV = R::NV;
-    extern __shared__ __align__(16) unsigned char bl_raw[];
-    Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
-    float* s_red = reinterpret_cast<float*>(bl_raw + 2 * sizeof(Stage<CH>));
-    __shared__ int s_id[2][BL_BATCH];
-    __shared__ int s_max[BL_NT / 32];
-    __shared__ int s_bid[BL_NT / 32][4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
-    const int tile = blockIdx.y * gxt + blockIdx.x;
-    const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const bool inside = px < W && py < H;
-    const long long pix = (long long)py * W + px;
-    const long long hw = (long long)H * W;
-
-    const int2 range = tile_range[tile];
-    const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
-    int wmax = lc;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int maxc = 0;
-#pragma unroll
-    for (int w = 0; w < BL_NT / 32; ++w) maxc = max(maxc, s_max[w]);
-    const int nb = (maxc + BL_BATCH - 1) / BL_BATCH;
-
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    float dpix[CH];
-    f32x2 dpix2[CH / 2], S2[CH / 2];  // cotangent and suffix colour, two channels per 64-bit register pair
-    float bgdot = 0.f;
-#pragma unroll
-    for (int k = 0; k < CH; ++k) {
-        dpix[k] = (inside && k < c_valid) ? dL_dimage[k * hw + pix] : 0.f;
-        bgdot = fmaf(bg, dpix[k], bgdot);
-    }
-#pragma unroll
-    for (int k = 0; k < CH; k += 2) {
-        dpix2[k / 2] = pk2(dpix[k], dpix[k + 1]);
-        S2[k / 2] = pk2(0.f, 0.f);
-    }
-    const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
-
-    // this lane's role at flush time: row `lane` of the buffer = value (lane % NV) of visit (lane / NV)
-    const int my_k = lane / NV, my_v = lane - my_k * NV;
-    float* gptr = nullptr;
-    int gstride = 0;
-    if (lane < R::K * NV) {
-        if (my_v < 6) {
-            if (geom_grads) { gptr = grec + my_v; gstride = 8; }
-        } else if (my_v - 6 < c_valid) {
-            gptr = gfeat + foff + (my_v - 6);
-            gstride = fstride;
-        }
-    }
-    float* rb = s_red + warp * R::FLOATS;
-    int* bidw = s_bid[warp];
-    int nbuf = 0;
-
-    auto flush = [&]() {
-        __syncwarp();
-        if (lane < nbuf * NV) {
-            const float4* r = reinterpret_cast<const float4*>(rb + lane * R::STRIDE);
-            const float4 r0 = r[0];
-            f32x2 a = pk2(r0.x, r0.y), c = pk2(r0.z, r0.w);
-#pragma unroll
-            for (int i = 1; i < 8; ++i) {
-                const float4 x = r[i];
-                a = add2(a, pk2(x.x, x.y));
-                c = add2(c, pk2(x.z, x.w));
-            }
-            float slo, shi;
-            upk2(add2(a, c), slo, shi);
-            const float sum = slo + shi;
-            if (gptr != nullptr && sum != 0.f) atomicAdd(gptr + (long long)bidw[my_k] * gstride, sum);
-        }
-        __syncwarp();
-        nbuf = 0;
-    };
-
-    // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
-    int id_next = 0;
-    if (nb > 0) {
-        if (tid < maxc) {
-            const int id = ids[range.x + maxc - 1 - tid];
-            s_id[0][tid] = id;
-            stage_issue(stages[0], tid, id, rec, featp, fstride, foff);
-        }
-        cp_async_commit();
-        if (BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - (BL_BATCH + tid)];
-    }
-    for (int b = 0; b < nb; ++b) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (b + 1 < nb) {
-            if ((b + 1) * BL_BATCH + tid < maxc) {
-                s_id[(b + 1) & 1][tid] = id_next;
-                stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
-            }
-            cp_async_commit();
-            if ((b + 2) * BL_BATCH + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * BL_BATCH + tid)];
-        }
-        const Stage<CH>& st = stages[b & 1];
-        const int* sid = s_id[b & 1];
-        const int cnt = min(BL_BATCH, maxc - b * BL_BATCH);
-        const int pos0 = maxc - 1 - b * BL_BATCH;  // list position of slot 0 of this batch
-        if (pos0 - (cnt - 1) >= wmax) continue;    // whole batch lies beyond every pixel of this warp
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-            bool hit = false;
-            if (k0 + lane < cnt) {
-                const float4 r0 = st.rec[2 * (k0 + lane)];
-                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
-                                  (r0.y - r1.w > wy1);
-                hit = !miss && (pos0 - (k0 + lane) < wmax);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = k0 + __ffs(m) - 1;
-                m &= m - 1;
-                const float4 r0 = st.rec[2 * j];
-                const float4 r1 = st.rec[2 * j + 1];
-                const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
-                const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
-                const float Graw = ex2_approx(fmul(power, kLog2e));
-                const float araw = fmin_ftz(fmul(r1.y, Graw), kAlphaMax);
-                // alpha_blending.cu:185-187 (pos < lc) and :190-203 (power / alpha tests)
-                const bool valid = (pos0 - j < lc) && !(power > 0.0f) && !(araw < kAlphaMin);
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                const float alpha = valid ? araw : 0.0f;
-                const float G = valid ? Graw : 0.0f;
-                const float rinv = rcp_approx(1.0f - alpha);  // == 1 for a failing pair
-                T = T * rinv;                                  // :205
-                const float wgt = alpha * T;
-                float* w = rb + nbuf * (NV * R::STRIDE) + lane;
-                // channel math on packed pairs (FFMA2/FMUL2): per pair of channels
-                //   e = f T - S / (1 - alpha);  dL_dalpha += e . dpix;  S += f alpha T;  dL_dfeature = alpha T dpix
-                const f32x2 T2 = pk2(T, T), W2 = pk2(wgt, wgt), NR2 = pk2(-rinv, -rinv);
-                f32x2 dacc = pk2(nbg * rinv, 0.f);             // :222-229 (background term)
-#pragma unroll
-                for (int k = 0; k < CH; k += 4) {
-                    const float4 fv = *reinterpret_cast<const float4*>(&st.feat[j * CH + k]);
-                    const f32x2 fa = pk2(fv.x, fv.y), fb = pk2(fv.z, fv.w);
-                    const f32x2 ea = fma2(S2[k / 2], NR2, mul2(fa, T2));           // :213-217
-                    const f32x2 eb = fma2(S2[k / 2 + 1], NR2, mul2(fb, T2));
-                    dacc = fma2(ea, dpix2[k / 2], dacc);
-                    dacc = fma2(eb, dpix2[k / 2 + 1], dacc);
-                    S2[k / 2] = fma2(fa, W2, S2[k / 2]);
-                    S2[k / 2 + 1] = fma2(fb, W2, S2[k / 2 + 1]);
-                    float w0, w1, w2, w3;
-                    upk2(mul2(W2, dpix2[k / 2]), w0, w1);                          // :218-219
-                    upk2(mul2(W2, dpix2[k / 2 + 1]), w2, w3);
-                    w[(6 + k) * R::STRIDE] = w0;
-                    w[(7 + k) * R::STRIDE] = w1;
-                    w[(8 + k) * R::STRIDE] = w2;
-                    w[(9 + k) * R::STRIDE] = w3;
-                }
-                float dlo, dhi;
-                upk2(dacc, dlo, dhi);
-                const float dL_dalpha = dlo + dhi;
-                const float dL_dG = r1.y * dL_dalpha;  // :231
-                const float gdl = G * dL_dG;
-                w[0 * R::STRIDE] = gdl * (-dx * r0.z - dy * r0.w);  // :232-237
-                w[1 * R::STRIDE] = gdl * (-dy * r1.x - dx * r0.w);
-                w[2 * R::STRIDE] = -0.5f * gdl * dx * dx;            // :238-242
-                w[3 * R::STRIDE] = -gdl * dx * dy;
-                w[4 * R::STRIDE] = -0.5f * gdl * dy * dy;
-                w[5 * R::STRIDE] = G * dL_dalpha;                    // :243
-                if (lane == 0) bidw[nbuf] = sid[j];
-                if (++nbuf == R::K) flush();
-            }
-        }
-    }
-    if (nbuf > 0) flush();
-    cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward, v3: pixel-parallel replay + Gaussian-parallel gradient accumulation
+// backward: pixel-parallel replay + Gaussian-parallel gradient accumulation
 // ------------------------------------------------------------------------------------------------
 // Every gradient of a (pixel p, Gaussian g) pair is a product of two scalars that need the
 // sequential per-pixel replay,
@@ -641,18 +429,18 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
                 hit = !miss && (pos0 - (k0 + lane) < wmax);
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = k0 + __ffs(m) - 1;
-                m &= m - 1;
+            // alpha of a pair (alpha_blending.cu:190-203); the pos < lc test is :185-187
+            auto pair_eval = [&](int j, float& Graw, float& araw) -> bool {
                 const float4 r0 = st.rec[2 * j];
                 const float4 r1 = st.rec[2 * j + 1];
                 const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
                 const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
-                const float Graw = ex2_approx(fmul(power, kLog2e));
-                const float araw = fmin_ftz(fmul(r1.y, Graw), kAlphaMax);
-                // alpha_blending.cu:185-187 (pos < lc) and :190-203 (power / alpha tests)
-                const bool valid = (pos0 - j < lc) && !(power > 0.0f) && !(araw < kAlphaMin);
-                if (!__any_sync(0xffffffffu, valid)) continue;
+                Graw = ex2_approx(fmul(power, kLog2e));
+                araw = fmin_ftz(fmul(r1.y, Graw), kAlphaMax);
+                return (pos0 - j < lc) && !(power > 0.0f) && !(araw < kAlphaMin);
+            };
+            // sequential replay step of one visit; parks (X, w) for phase 2
+            auto replay = [&](int j, bool valid, float Graw, float araw) {
                 const float alpha = valid ? araw : 0.0f;
                 const float G = valid ? Graw : 0.0f;
                 const float rinv = rcp_approx(1.0f - alpha);  // == 1 for a failing pair
@@ -680,11 +468,27 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
                 *qw_wr++ = j;
                 if (++cnt == BW_GQ) {
                     bwd_reduce_group<CH, B>(BW_GQ, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
-                                         geom_grads);
+                                            geom_grads);
                     cnt = 0;
                     xw_wr = xw + lane;
                     qw_wr = qw;
                 }
+            };
+            // Two hits per iteration: their alpha evaluations (LDS -> 7 dependent FP32 ops -> MUFU.EX2 -> min ->
+            // compare -> vote) are independent and interleave; only the replay steps are sequential.
+            while (m) {
+                const int j1 = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const bool two = m != 0u;
+                const int j2 = two ? k0 + __ffs(m) - 1 : j1;
+                m &= m - 1;  // no-op when m == 0
+                float G1, a1, G2, a2;
+                const bool v1 = pair_eval(j1, G1, a1);
+                const bool v2 = pair_eval(j2, G2, a2) && two;
+                const bool any1 = __any_sync(0xffffffffu, v1);
+                const bool any2 = __any_sync(0xffffffffu, v2);
+                if (any1) replay(j1, v1, G1, a1);
+                if (any2) replay(j2, v2, G2, a2);
             }
         }
         if (cnt > 0) {  // the stage buffer is recycled after this batch
@@ -713,27 +517,6 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
     blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
                                                     final_T, ncontrib, image);
     return check_launch("alpha_blending_fwd");
-}
-
-// A/B switch for profiling runs: MSB_BWD_V2=1 selects the v2 backward kernel
-static bool blend_use_bwd_v2() {
-    static const int v = [] { const char* e = getenv("MSB_BWD_V2"); return (e && e[0] == '1') ? 1 : 0; }();
-    return v != 0;
-}
-
-template <int CH, int KV>
-static int launch_bwd_v2(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
-                         const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
-                         const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
-    const size_t smem = 2 * sizeof(Stage<CH>) + (size_t)(BL_NT / 32) * BwdRed<CH, KV>::FLOATS * sizeof(float);
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel_v2<CH, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
-    }
-    blend_bwd_kernel_v2<CH, KV><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                           final_T, ncontrib, dL_dimage, grec, gfeat, geom);
-    return check_launch("alpha_blending_bwd");
 }
 
 // A/B switch for profiling runs (CH = 4).  Measured on BASELINE config #3 (profiles/r1_ab_blend_bwd.md):
@@ -765,17 +548,13 @@ template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
                       const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
-    if (blend_use_bwd_v2()) {
-        constexpr int KV = CH == 4 ? 2 : 32 / (6 + CH);
-        return launch_bwd_v2<CH, KV>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib,
-                                     dL_dimage, grec, gfeat, geom);
-    }
 #define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, grec, gfeat, geom
     if constexpr (CH == 4) {
         switch (blend_bwd_cfg()) {
-            case 1: return launch_bwd_cfg<CH, 128, 0>(MSB_BWD_ARGS);
+            case 1: return launch_bwd_cfg<CH, 128, 3>(MSB_BWD_ARGS);
+            case 2: return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
             case 3: return launch_bwd_cfg<CH, 128, 4>(MSB_BWD_ARGS);
-            default: return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
+            default: return launch_bwd_cfg<CH, 256, 3>(MSB_BWD_ARGS);
         }
     } else {
         return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
