@@ -261,7 +261,20 @@ def run_gpu(args, api, impl):
             timing, _lib.TIMING = _lib.TIMING, None
             _render.OVERLAP = prev
             serial_ms = e0.elapsed_time(e1) / args.steps
-            timing = (timing, serial_ms)
+            # the same per-call events with the two-stream schedule on: how long each call takes while it
+            # shares the SMs with the other stream's kernels
+            step(*dev_in)
+            barrier_sync(world)
+            _lib.TIMING = []
+            step(*dev_in)
+            barrier_sync(world)
+            ov, _lib.TIMING = _lib.TIMING, None
+            agg = {}
+            for name, a, b in ov:
+                d = agg.setdefault(name, [0.0, 0])
+                d[0] += a.elapsed_time(b)
+                d[1] += 1
+            timing = (timing, serial_ms, {k: round(v[0] / v[1], 4) for k, v in agg.items()})
         # e2e: per step H2D of the step's inputs (cameras + cotangent) from pinned memory, D2H of the loss
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         barrier_sync(world)
@@ -305,8 +318,9 @@ def run_gpu(args, api, impl):
     }
     if ours:
         out["gpu_launches"] = launches
-        timing, serial_ms = timing
+        timing, serial_ms, overlapped = timing
         out["serial_ms_per_step"] = serial_ms  # same step with the two-stream overlap switched off (stage timings)
+        out["stage_ms_two_stream"] = overlapped  # per-call durations while overlapping with the other stream
         out.update(stage_report(timing, args, api, params, cams_host[0], G, clocks, V))
         if fused and not args.no_steps_api:
             s_ms, s_val, s_e2e, _, _, _ = measure(step_steps)

@@ -18,7 +18,7 @@ CMD="python bench.py --steps 1 --warmup 3 --views 1 --no-cpu-baseline --no-steps
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/launches_$TAG.out 2>&1
 echo "launch list rc=$?"; tail -1 gpurun_out/launches_$TAG.out | cut -c1-300
-echo "== ncu full capture (4th step = first timed step: 12 matching launches per step)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"blend_bwd|blend_fwd|render_pre|onesweep|duplicate|keygen" -s 36 -c 12 -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/prof_$TAG.out 2>&1
+echo "== ncu full capture (4th step = first timed step: 14 matching launches per step)"
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"blend_bwd|blend_fwd|render_pre|onesweep|duplicate|keygen|scan_offsets|tile_range" -s 42 -c 14 -o gpurun_out/prof_$TAG -f $CMD > gpurun_out/prof_$TAG.out 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/prof_$TAG.out | cut -c1-300
 ls -la gpurun_out/ | head -40
