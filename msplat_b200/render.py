@@ -156,7 +156,7 @@ class _RenderSHViews(torch.autograd.Function):
                 ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, W, H),), dtype=torch.uint8, device=dev)
                 final_T = torch.empty((H, W), dtype=f32, device=dev)
                 ncontrib = torch.empty((H, W), dtype=i32, device=dev)
-                nk = 6 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0
+                nk = 4 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0  # keygen, offsets, duplicate, ranges + passes
                 with torch.cuda.stream(side if side is not None else main):
                     _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius),
                               ptr(tiles), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))

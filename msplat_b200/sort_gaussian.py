@@ -38,7 +38,7 @@ def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, til
                 raise RuntimeError(f"sort_gaussian: {M} tile intersections exceed the supported 2^30")
             idx_sorted = torch.empty((M,), dtype=torch.int32, device=dev)
             ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, int(W), int(H)),), dtype=torch.uint8, device=dev)
-            nk = 6 + L.msb_sort_num_passes(int(W), int(H)) if (M > 0 and P > 0) else 0  # keygen, 3 scan, duplicate, ranges + passes
+            nk = 4 + L.msb_sort_num_passes(int(W), int(H)) if (M > 0 and P > 0) else 0  # keygen, offsets, duplicate, ranges + passes
             _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(u), ptr(d), ptr(r), ptr(t), P,
                       M, int(W), int(H), ptr(idx_sorted), ptr(tile_range), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
     return idx_sorted, tile_range

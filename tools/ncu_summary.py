@@ -40,7 +40,10 @@ def launches(path, first="render_pre_fwd", last="render_pre_bwd", which=3):
 def full(path):
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
-    cols = [("ms", "gpu__time_duration.sum"), ("DRAM rd MB", "dram__bytes_read.sum"), ("DRAM wr MB", "dram__bytes_write.sum"),
+    units = rows[1]
+    scale = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0,
+             "Gbyte": 1e3}
+    cols = [("us", "gpu__time_duration.sum"), ("DRAM rd MB", "dram__bytes_read.sum"), ("DRAM wr MB", "dram__bytes_write.sum"),
             ("DRAM %", "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
             ("issue active %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
             ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
@@ -55,7 +58,7 @@ def full(path):
         for _, b in cols:
             v = r[hdr.index(b)].replace(",", "")
             try:
-                vals.append(f"{float(v):.4g}")
+                vals.append(f"{float(v) * scale.get(units[hdr.index(b)], 1.0):.4g}")
             except ValueError:
                 vals.append(v)
         print(f"| `{name}` | " + " | ".join(vals) + " |")
