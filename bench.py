@@ -218,7 +218,8 @@ def run_gpu(args, api, impl):
         for p_ in params:
             p_.grad = None
         images = api.rasterization_sh_views(*params, intrs, extrs, W, H, 0.0, with_depth=True,
-                                            grad_sync=(world > 1))  # grads come back summed over the ranks
+                                            grad_sync=(world > 1),  # grads come back summed over the ranks
+                                            grad_chunks=args.grad_chunks)
         loss = (images * G_).sum()
         loss.backward()
         return loss.detach()
@@ -498,6 +499,8 @@ def main():
     ap.add_argument("--api", default="fused", choices=["fused", "steps"],
                     help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
     ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
+    ap.add_argument("--grad-chunks", type=int, default=3,
+                    help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "oracle":

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
                 const float G = ex2_approx(fmul(power, kLog2e));
                 const float alpha = fmin_ftz(fmul(r1.y, G), kAlphaMax);
                 const bool ok = !done && !(power > 0.0f) && !(alpha < kAlphaMin);
+                if (!__any_sync(0xffffffffu, ok)) continue;  // ~1 visit in 5: box hit, but no pixel of the warp blends
                 const float nT = fmul(T, fadd(-alpha, 1.0f));
                 const bool term = ok && (nT < kTmin);  // alpha_blending.cu:90-94: entry not blended
                 const bool blend = ok && !term;

@@ -354,6 +354,40 @@ def test_sort_edge_cases(ms):
     assert torch.equal(tr[:, 1], torch.arange(1, 32401, dtype=torch.int32, device=DEV))
 
 
+def test_sort_compaction_edge_cases(ms):
+    """The sort drops non-emitting Gaussians before its depth passes (device-side count Pc):
+    Pc == 0 with M > 0 (phantom slots only), a single tile (no tile-digit bits), and a cloud whose
+    emitters are a short run in the middle of long culled stretches (empty keygen CTAs)."""
+    def check(uv, depth, radius, tiles, W, H):
+        ids, tr = ms.sort_gaussian(uv.to(DEV), depth.to(DEV), W, H, radius.to(DEV), tiles.to(DEV))
+        ids_o, tr_o = oracle.sort_gaussian(uv, depth, W, H, radius, tiles)
+        assert torch.equal(cpu(tr), tr_o), "tile_range differs from the oracle"
+        assert torch.equal(cpu(ids), ids_o), "sorted ids differ from the oracle"
+        return ids_o
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32)
+    # only phantom slots
+    ids = check(torch.tensor([[3.0, 3.0], [40.0, 9.0]]), torch.tensor([[1.0], [2.0]]), i32([0, -1]), i32([3, 2]), 64, 32)
+    assert ids.tolist() == [0, 0, 0, 0, 0]
+    # one tile
+    g = torch.Generator().manual_seed(3)
+    P = 500
+    uv = torch.rand(P, 2, generator=g) * 16
+    depth = torch.rand(P, 1, generator=g) + 0.5
+    radius = (torch.rand(P, generator=g) * 4).to(torch.int32)  # some zeros
+    tiles = (radius > 0).to(torch.int32)
+    check(uv, depth, radius, tiles, 16, 16)
+    # 50 emitters inside 300k culled Gaussians
+    P = 300_000
+    uv = torch.rand(P, 2, generator=g) * torch.tensor([640.0, 480.0])
+    depth = torch.rand(P, 1, generator=g) * 10 + 0.1
+    radius = torch.zeros(P, dtype=torch.int32)
+    radius[100_000:100_050] = 20
+    from oracle.steps import get_rect
+    x0, y0, x1, y1 = get_rect(uv, radius, 640, 480)
+    tiles = ((x1 - x0) * (y1 - y0)).to(torch.int32) * (radius > 0)
+    check(uv, depth, radius, tiles, 640, 480)
+
+
 def test_sort_vs_reference(ms, ref_msplat):
     """gaussian_ids_sorted and tile_range bit-exact vs cumsum + key kernel + torch.sort + gather."""
     for (P, W, H, mul, tie) in [(300000, 1920, 1080, 1.5, False), (100000, 800, 800, 1.0, True),
