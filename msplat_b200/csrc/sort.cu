@@ -370,7 +370,31 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
     }
     int total;
     const int excl = block_excl_scan<SC_NT>(sum, s_warp, total);
-    if (warp == 0) {
+    if (gridDim.x <= 4096) {
+        // few tiles (all resident at once on this GPU up to ~1.8 M emitters): every tile publishes its total
+        // and sums the totals of ALL tiles before it -- one round trip instead of a look-back chain
+        __shared__ unsigned int s_part[SC_NT / 32];
+        if (threadIdx.x == 0) st_relaxed(status + tile, RS_FLAG_PRE | (unsigned)total);
+        unsigned int part = 0;
+        for (int j = threadIdx.x; j < tile; j += SC_NT) {
+            unsigned int w = ld_relaxed(status + j);
+            while (w == 0u) {
+                __nanosleep(20);
+                w = ld_relaxed(status + j);
+            }
+            part += w & RS_VALUE_MASK;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int pre = 0;
+#pragma unroll
+            for (int w = 0; w < SC_NT / 32; ++w) pre += s_part[w];
+            s_prefix = pre;
+        }
+    } else if (warp == 0) {
         unsigned int pre = 0;
         if (tile > 0) {
             if (lane == 0) st_relaxed(status + tile, RS_FLAG_AGG | (unsigned)total);
@@ -409,7 +433,18 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
 // phase 2d: duplication in depth order + histograms of the tile-digit passes
 // ------------------------------------------------------------------------------------------------
 constexpr int DUP_NT = 256;
-constexpr int DUP_SMALL = 8;
+constexpr int DUP_COOP = 64;  // footprints up to this many tiles are expanded cooperatively
+
+// tile-digit histograms of one emitted entry per lane (valid lanes only)
+__device__ __forceinline__ void dup_hist(unsigned int* s_hist, unsigned int tile, bool valid, int npass) {
+    if (valid) atomicAdd(&s_hist[tile & 255u], 1u);  // low digit: neighbouring entries are neighbouring tiles
+    for (int p = 1; p < npass; ++p) {
+        // higher digits are (almost) warp-uniform: one aggregated add per distinct value
+        const unsigned d = valid ? ((tile >> (8 * p)) & 255u) : 0xffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], (unsigned)__popc(peers));
+    }
+}
 
 __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* __restrict__ pcount,
                                                            const int* __restrict__ order /*[Pc] depth order*/,
@@ -431,6 +466,7 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* _
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && Z)
         for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256], Z);
+    const bool packable = gx < 4096;  // x0, y0 < 4096 fit the packed shuffle word (y0 < gy is not bounded by it)
     const long long nchunks = ((long long)P + DUP_NT - 1) / DUP_NT;
     for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const long long i = chunk * DUP_NT + threadIdx.x;
@@ -444,23 +480,50 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* _
             w = r.z;
             n = r.w;
         }
-        // small footprints: each lane emits its own run
-        if (n > 0 && n <= DUP_SMALL) {
-            int tx = x0, ty = y0;
-            for (int e = 0; e < n; ++e) {
-                const unsigned int tile = (unsigned)(ty * gx + tx);
-                keys[start + e] = tile;
-                vals[start + e] = id;
-                for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & 255u)], 1u);
-                if (++tx == x0 + w) {
-                    tx = x0;
-                    ++ty;
-                }
-            }
+        // ---- footprints of up to DUP_COOP tiles: load-balanced expansion ----------------------------------
+        // The warp's Gaussians own consecutive output runs; lane L emits entry e = base + L of the
+        // concatenation, finds its source lane by binary search over the exclusive prefix of n (5 shuffles)
+        // and fetches {output offset, x0 | y0, w | magic, id} with 4 more: stores are coalesced and no lane
+        // idles behind a neighbour's larger footprint.  r / w for r w < 4096 is (r m) >> 12, m = 4096 / w + 1.
+        const bool coop = packable && n > 0 && n <= DUP_COOP && w <= DUP_COOP && y0 < (1 << 19);
+        const int nc = coop ? n : 0;
+        int rel = nc;  // exclusive prefix of nc over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, rel, o);
+            if (lane >= o) rel += v;
         }
-        // large footprints: the whole warp emits one Gaussian at a time (reference: one thread
+        const int total = __shfl_sync(0xffffffffu, rel, 31);
+        rel -= nc;
+        const int delta = start - rel;
+        const int pxy = x0 | (y0 << 12);
+        const int wm = w | ((4096 / max(w, 1) + 1) << 8);
+        for (int base = 0; base < total; base += 32) {
+            const int e = base + lane;
+            const bool valid = e < total;
+            int src = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, rel, src + step);
+                if (v <= e) src += step;
+            }
+            const int srel = __shfl_sync(0xffffffffu, rel, src);
+            const int sdelta = __shfl_sync(0xffffffffu, delta, src);
+            const int sxy = __shfl_sync(0xffffffffu, pxy, src);
+            const int swm = __shfl_sync(0xffffffffu, wm, src);
+            const int sid = __shfl_sync(0xffffffffu, id, src);
+            const int r = e - srel;
+            const int sw = swm & 255, ry = (r * (swm >> 8)) >> 12, rx = r - ry * sw;
+            const unsigned int tile = (unsigned)(((sxy >> 12) + ry) * gx + (sxy & 4095) + rx);
+            if (valid) {
+                keys[sdelta + e] = tile;
+                vals[sdelta + e] = sid;
+            }
+            dup_hist(s_hist, tile, valid, npass);
+        }
+        // ---- larger footprints: the whole warp emits one Gaussian at a time (reference: one thread
         // serially writes up to T entries, sort_gaussian.cu:35-42)
-        unsigned big = __ballot_sync(0xffffffffu, n > DUP_SMALL);
+        unsigned big = __ballot_sync(0xffffffffu, n > 0 && !coop);
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
@@ -470,12 +533,16 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* _
             const int by0 = __shfl_sync(0xffffffffu, y0, src);
             const int bw = __shfl_sync(0xffffffffu, w, src);
             const int bid = __shfl_sync(0xffffffffu, id, src);
-            for (int e = lane; e < bn; e += 32) {
+            for (int e0 = 0; e0 < bn; e0 += 32) {
+                const int e = e0 + lane;
+                const bool valid = e < bn;
                 const int ry = e / bw, rx = e - ry * bw;
                 const unsigned int tile = (unsigned)((by0 + ry) * gx + bx0 + rx);
-                keys[bstart + e] = tile;
-                vals[bstart + e] = bid;
-                for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + ((tile >> (8 * p)) & 255u)], 1u);
+                if (valid) {
+                    keys[bstart + e] = tile;
+                    vals[bstart + e] = bid;
+                }
+                dup_hist(s_hist, tile, valid, npass);
             }
         }
     }
