@@ -214,6 +214,70 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
     for (int i = 4 * nvec + threadIdx.x; i < count; i += NT) dst[i] = smem[i];
 }
 
+// ---- slab sets: TMA bulk copies for full blocks, per-thread path for the ragged last block ----------
+// d[i] = {shared-memory slab, global [P, k] array, k}.  A full block (rows == NT, 16-byte aligned
+// bases) moves all slabs with cp.async.bulk issued by thread 0 and waits on one mbarrier (loads) or
+// on the bulk group (stores); otherwise slab_load / slab_store.  Both end with the block in sync.
+struct SlabIn {
+    float* s;
+    const float* g;
+    int k;
+};
+struct SlabOut {
+    const float* s;
+    float* g;
+    int k;
+};
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0ull; }
+
+template <int NT, int N>
+__device__ __forceinline__ void slabs_load(unsigned long long* bar, const SlabIn (&d)[N], long long row0, int rows) {
+    bool full = rows == NT;
+#pragma unroll
+    for (int i = 0; i < N; ++i) full = full && al16(d[i].g);
+    if (threadIdx.x == 0 && full) mbar_init(bar, 1);
+    __syncthreads();
+    if (full) {
+        if (threadIdx.x == 0) {
+            unsigned bytes = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) bytes += (unsigned)(d[i].k * NT * sizeof(float));
+            mbar_expect_tx(bar, bytes);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                bulk_g2s(d[i].s, d[i].g + row0 * d[i].k, (unsigned)(d[i].k * NT * sizeof(float)), bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) slab_load<NT>(d[i].s, d[i].g, row0 * d[i].k, rows * d[i].k);
+        __syncthreads();
+    }
+}
+
+// Call after the threads have written their rows into the shared-memory slabs (no barrier needed before).
+template <int NT, int N>
+__device__ __forceinline__ void slabs_store(const SlabOut (&d)[N], long long row0, int rows) {
+    bool full = rows == NT;
+#pragma unroll
+    for (int i = 0; i < N; ++i) full = full && al16(d[i].g);
+    if (full) {
+        fence_async_smem();  // this thread's slab writes -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                bulk_s2g(d[i].g + row0 * d[i].k, d[i].s, (unsigned)(d[i].k * NT * sizeof(float)));
+            bulk_commit();
+            bulk_wait_read();  // shared memory must stay valid until the copy engine has read it
+        }
+    } else {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < N; ++i) slab_store<NT>(d[i].g, d[i].s, row0 * d[i].k, rows * d[i].k);
+    }
+}
+
 // ---- warp helpers -----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -8,7 +8,8 @@
 //
 // Layout / roofline: every tensor of the msplat API is row-major [P, K] with small K.  A block
 // of 256 threads owns 256 consecutive Gaussians; each [256, K] slab is contiguous, so it is
-// moved HBM <-> shared memory with coalesced 16-byte accesses (common.cuh slab_load/store) and
+// moved HBM <-> shared memory by TMA bulk copies (common.cuh slabs_load/slabs_store; coalesced
+// 16-byte per-thread accesses for the ragged last block) and
 // each thread then works on its own row from shared memory.  Outputs for culled / invisible /
 // degenerate Gaussians are written as explicit zeros (the reference relies on pre-zeroed
 // tensors: project_point.cu:161-162, ewa_project.cu:274-276), so no memset pass is needed.
@@ -32,8 +33,11 @@ __global__ void __launch_bounds__(NT) project_point_fwd_kernel(int P, const floa
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s, xyz, row0 * 3, rows * 3);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s, xyz, 3}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float u = 0.f, v = 0.f, d = 0.f;
     if (t < rows) {
@@ -46,8 +50,10 @@ __global__ void __launch_bounds__(NT) project_point_fwd_kernel(int P, const floa
         s[2 * t + 1] = v;
         depth[row0 + t] = d;
     }
-    __syncthreads();
-    slab_store<NT>(uv, s, row0 * 2, rows * 2);
+    {
+        const SlabOut out[] = {{s, uv, 2}};
+        slabs_store<NT>(out, row0, rows);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -64,9 +70,11 @@ __global__ void __launch_bounds__(NT) project_point_bwd_kernel(
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s_xyz, xyz, row0 * 3, rows * 3);
-    slab_load<NT>(s_guv, dL_duv, row0 * 2, rows * 2);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_xyz, xyz, 3}, {s_guv, dL_duv, 2}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float cam[16];
 #pragma unroll
@@ -82,8 +90,10 @@ __global__ void __launch_bounds__(NT) project_point_bwd_kernel(
         s_xyz[3 * t + 1] = dy;
         s_xyz[3 * t + 2] = dz;
     }
-    __syncthreads();
-    slab_store<NT>(dL_dxyz, s_xyz, row0 * 3, rows * 3);
+    {
+        const SlabOut out[] = {{s_xyz, dL_dxyz, 3}};
+        slabs_store<NT>(out, row0, rows);
+    }
     if (CAM) cam_reduce_atomic(cam, dL_dintr, dL_dextr, s_red);
 }
 
@@ -99,9 +109,11 @@ __global__ void __launch_bounds__(NT) cov3d_fwd_kernel(int P, const float* __res
     float* s_quat = s + NT * 3;
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
-    slab_load<NT>(s_scale, scale, row0 * 3, rows * 3);
-    slab_load<NT>(s_quat, quat, row0 * 4, rows * 4);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_scale, scale, 3}, {s_quat, quat, 4}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (t < rows && (visible == nullptr || visible[row0 + t])) {
@@ -115,8 +127,10 @@ __global__ void __launch_bounds__(NT) cov3d_fwd_kernel(int P, const float* __res
         o[1] = make_float2(cv[2], cv[3]);
         o[2] = make_float2(cv[4], cv[5]);
     }
-    __syncthreads();
-    slab_store<NT>(cov3d, s, row0 * 6, rows * 6);
+    {
+        const SlabOut out[] = {{s, cov3d, 6}};
+        slabs_store<NT>(out, row0, rows);
+    }
 }
 
 __global__ void __launch_bounds__(NT) cov3d_bwd_kernel(int P, const float* __restrict__ scale,
@@ -131,10 +145,11 @@ __global__ void __launch_bounds__(NT) cov3d_bwd_kernel(int P, const float* __res
     float* s_g = s + NT * 7;
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
-    slab_load<NT>(s_scale, scale, row0 * 3, rows * 3);
-    slab_load<NT>(s_quat, quat, row0 * 4, rows * 4);
-    slab_load<NT>(s_g, dL_dcov3d, row0 * 6, rows * 6);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_scale, scale, 3}, {s_quat, quat, 4}, {s_g, dL_dcov3d, 6}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     if (t < rows && (visible == nullptr || visible[row0 + t])) {
@@ -151,9 +166,10 @@ __global__ void __launch_bounds__(NT) cov3d_bwd_kernel(int P, const float* __res
         s_scale[3 * t + 2] = ds[2];
         reinterpret_cast<float4*>(s_quat)[t] = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
-    __syncthreads();
-    slab_store<NT>(dL_dscale, s_scale, row0 * 3, rows * 3);
-    slab_store<NT>(dL_dquat, s_quat, row0 * 4, rows * 4);
+    {
+        const SlabOut out[] = {{s_scale, dL_dscale, 3}, {s_quat, dL_dquat, 4}};
+        slabs_store<NT>(out, row0, rows);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -174,10 +190,11 @@ __global__ void __launch_bounds__(NT) ewa_fwd_kernel(int P, const float* __restr
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s_xyz, xyz, row0 * 3, rows * 3);
-    slab_load<NT>(s_cov, cov3d, row0 * 6, rows * 6);
-    slab_load<NT>(s_uv, uv, row0 * 2, rows * 2);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_xyz, xyz, 3}, {s_cov, cov3d, 6}, {s_uv, uv, 2}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float cx = 0.f, cy = 0.f, cz = 0.f;
     int rad = 0, til = 0;
@@ -200,8 +217,10 @@ __global__ void __launch_bounds__(NT) ewa_fwd_kernel(int P, const float* __restr
         radius[row0 + t] = rad;
         tiles[row0 + t] = til;
     }
-    __syncthreads();
-    slab_store<NT>(conic, s_xyz, row0 * 3, rows * 3);
+    {
+        const SlabOut out[] = {{s_xyz, conic, 3}};
+        slabs_store<NT>(out, row0, rows);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -226,10 +245,11 @@ __global__ void __launch_bounds__(NT) ewa_bwd_kernel(int P, const float* __restr
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s_xyz, xyz, row0 * 3, rows * 3);
-    slab_load<NT>(s_cov, cov3d, row0 * 6, rows * 6);
-    slab_load<NT>(s_gc, dL_dconic, row0 * 3, rows * 3);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_xyz, xyz, 3}, {s_cov, cov3d, 6}, {s_gc, dL_dconic, 3}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float cam[16];
 #pragma unroll
@@ -257,9 +277,10 @@ __global__ void __launch_bounds__(NT) ewa_bwd_kernel(int P, const float* __restr
         o[1] = make_float2(dcv[2], dcv[3]);
         o[2] = make_float2(dcv[4], dcv[5]);
     }
-    __syncthreads();
-    slab_store<NT>(dL_dxyz, s_xyz, row0 * 3, rows * 3);
-    slab_store<NT>(dL_dcov3d, s_cov, row0 * 6, rows * 6);
+    {
+        const SlabOut out[] = {{s_xyz, dL_dxyz, 3}, {s_cov, dL_dcov3d, 6}};
+        slabs_store<NT>(out, row0, rows);
+    }
     if (CAM) cam_reduce_atomic(cam, dL_dintr, dL_dextr, s_red);
 }
 
@@ -280,10 +301,11 @@ __global__ void __launch_bounds__(NT) preprocess_fwd_kernel(
     const int rows = (int)min((long long)NT, P - row0);
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s_xyz, xyz, row0 * 3, rows * 3);
-    slab_load<NT>(s_scale, scale, row0 * 3, rows * 3);
-    slab_load<NT>(s_quat, quat, row0 * 4, rows * 4);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_xyz, xyz, 3}, {s_scale, scale, 3}, {s_quat, quat, 4}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float u = 0.f, v = 0.f, d = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
     int rad = 0, til = 0;
@@ -312,9 +334,10 @@ __global__ void __launch_bounds__(NT) preprocess_fwd_kernel(
         radius[row0 + t] = rad;
         tiles[row0 + t] = til;
     }
-    __syncthreads();
-    slab_store<NT>(uv, s, row0 * 2, rows * 2);
-    slab_store<NT>(conic, s + NT * 2, row0 * 3, rows * 3);
+    {
+        const SlabOut out[] = {{s, uv, 2}, {s + NT * 2, conic, 3}};
+        slabs_store<NT>(out, row0, rows);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -337,12 +360,11 @@ __global__ void __launch_bounds__(NT) preprocess_bwd_kernel(
     const long long row0 = (long long)blockIdx.x * NT;
     const int rows = (int)min((long long)NT, P - row0);
     const Cam c = load_cam(intr, extr);
-    slab_load<NT>(s_xyz, xyz, row0 * 3, rows * 3);
-    slab_load<NT>(s_scale, scale, row0 * 3, rows * 3);
-    slab_load<NT>(s_quat, quat, row0 * 4, rows * 4);
-    slab_load<NT>(s_guv, dL_duv, row0 * 2, rows * 2);
-    slab_load<NT>(s_gc, dL_dconic, row0 * 3, rows * 3);
-    __syncthreads();
+    __shared__ unsigned long long s_bar;
+    {
+        const SlabIn in[] = {{s_xyz, xyz, 3}, {s_scale, scale, 3}, {s_quat, quat, 4}, {s_guv, dL_duv, 2}, {s_gc, dL_dconic, 3}};
+        slabs_load<NT>(&s_bar, in, row0, rows);
+    }
     const int t = threadIdx.x;
     float cam[16];
 #pragma unroll
@@ -380,10 +402,10 @@ __global__ void __launch_bounds__(NT) preprocess_bwd_kernel(
         s_scale[3 * t + 2] = ds[2];
         reinterpret_cast<float4*>(s_quat)[t] = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
-    __syncthreads();
-    slab_store<NT>(dL_dxyz, s_xyz, row0 * 3, rows * 3);
-    slab_store<NT>(dL_dscale, s_scale, row0 * 3, rows * 3);
-    slab_store<NT>(dL_dquat, s_quat, row0 * 4, rows * 4);
+    {
+        const SlabOut out[] = {{s_xyz, dL_dxyz, 3}, {s_scale, dL_dscale, 3}, {s_quat, dL_dquat, 4}};
+        slabs_store<NT>(out, row0, rows);
+    }
     if (CAM) cam_reduce_atomic(cam, dL_dintr, dL_dextr, s_red);
 }
 
