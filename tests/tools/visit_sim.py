@@ -8,7 +8,7 @@ list is (a) a whole warp covering 8x4 pixels (blend.cu today), (b) a half-warp c
 lock-step over 32-entry windows of the staged batch, so a window costs max(popcount) visits.
 Uses the CPU oracle for geometry, sort and ncontrib.
 
-    python tools/visit_sim.py [scale_div=3]
+    python tests/tools/visit_sim.py [scale_div=3] [window=32]   (test infrastructure: it imports oracle/)
 """
 import math
 import os
@@ -17,7 +17,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 from msplat_b200.scenes import frustum_scene  # noqa: E402
