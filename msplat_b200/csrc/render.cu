@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
     const float* __restrict__ quat, const float* __restrict__ opacity, const float* __restrict__ shs,
     const float* __restrict__ intr, const float* __restrict__ extr, int W, int H, float nearest, float extent,
     float sh_bias, int clamp, float* __restrict__ rec, float* __restrict__ featp, float* __restrict__ uv,
-    float* __restrict__ depth, int* __restrict__ radius, int* __restrict__ tiles) {
+    float* __restrict__ depth, int* __restrict__ radius, int* __restrict__ tiles,
+    unsigned long long* __restrict__ total_tiles) {
     constexpr int D = sh_dim(DEG);
     constexpr int G = rp_gpb(DEG);
     constexpr int GS = G + 1;
@@ -167,6 +168,12 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
         }
     }
     list_append(til > 0, (unsigned)t, s_list, &s_cnt);
+    if (total_tiles != nullptr) {  // M = sum(tiles): sizes the sort output (replaces the separate count pass)
+        unsigned wsum = (unsigned)til;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        if ((tid & 31) == 0 && wsum) atomicAdd(total_tiles, (unsigned long long)wsum);
+    }
     __syncthreads();  // every thread is done with the input slabs
     if (t < rows) {
         float4* r = reinterpret_cast<float4*>(sm) + 2 * t;
@@ -535,6 +542,7 @@ struct RpFwdArgs {
     int clamp;
     float *rec, *featp, *uv, *depth;
     int *radius, *tiles;
+    unsigned long long* total_tiles;
 };
 
 template <int DEG>
@@ -551,7 +559,7 @@ static int rp_launch_fwd(const RpFwdArgs& a, cudaStream_t st) {
     render_pre_fwd_kernel<DEG><<<grid, RP_NT, smem, st>>>(a.P, a.Cs, a.Cpad, a.with_depth, a.xyz, a.scale, a.quat,
                                                           a.opacity, a.shs, a.intr, a.extr, a.W, a.H, a.nearest,
                                                           a.extent, a.sh_bias, a.clamp, a.rec, a.featp, a.uv, a.depth,
-                                                          a.radius, a.tiles);
+                                                          a.radius, a.tiles, a.total_tiles);
     return check_launch("render_preprocess_fwd");
 }
 
@@ -594,13 +602,18 @@ int msb_blend_cpad(int C);
 
 // Fused forward preprocess of the SH render path.  Outputs: rec [P,8] and featp [P,Cpad]
 // (Cpad = msb_blend_cpad(Cs + with_depth)) in the blend kernels' packed layout, uv [P,2],
-// depth [P], radius [P], tiles [P] (bit-identical to project_point / ewa_project).
+// depth [P], radius [P], tiles [P] (bit-identical to project_point / ewa_project).  total_dev (8 bytes of
+// device scratch) / total_host (pinned) are optional: when given, M = sum(tiles) is accumulated by the kernel
+// and copied asynchronously to *total_host, which replaces msb_sort_scan for this path.
 int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* opacity,
                               const float* shs, const float* intr, const float* extr, int P, int Cs, int D,
                               int with_depth, int W, int H, float nearest, float extent, float sh_bias, int clamp,
                               float* rec, float* featp, float* uv, float* depth, int32_t* radius, int32_t* tiles,
-                              void* stream) {
-    if (P == 0) return MSB_OK;
+                              long long* total_dev, long long* total_host, void* stream) {
+    if (P == 0) {
+        if (total_host) *total_host = 0;
+        return MSB_OK;
+    }
     const int deg = sh_degree_of(D);
     if (P < 0 || Cs < 0 || deg < 0 || W <= 0 || H <= 0)
         return set_error(MSB_ERR_ARG, "render_preprocess_fwd: bad size (D must be (deg+1)^2, deg <= 10)");
@@ -611,17 +624,33 @@ int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float*
           rp_al16(featp) && rp_al16(uv)))
         return set_error(MSB_ERR_ARG, "render_preprocess_fwd: 16-byte alignment");
     RpFwdArgs a{P, Cs, msb_blend_cpad(Cs + (with_depth ? 1 : 0)), with_depth ? 1 : 0, xyz, scale, quat, opacity, shs,
-                intr, extr, W, H, nearest, extent, sh_bias, clamp ? 1 : 0, rec, featp, uv, depth, radius, tiles};
+                intr, extr, W, H, nearest, extent, sh_bias, clamp ? 1 : 0, rec, featp, uv, depth, radius, tiles,
+                reinterpret_cast<unsigned long long*>(total_dev)};
     cudaStream_t st = (cudaStream_t)stream;
+    if ((total_dev == nullptr) != (total_host == nullptr))
+        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: total_dev and total_host go together");
+    if (total_dev) {
+        cudaError_t e = cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
+        if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: memset failed");
+    }
+    int rc = MSB_ERR_ARG;
     switch (deg) {
-#define MSB_RP_CASE(d) \
-    case d:            \
-        return rp_launch_fwd<d>(a, st);
+#define MSB_RP_CASE(d)                \
+    case d:                           \
+        rc = rp_launch_fwd<d>(a, st); \
+        break;
         MSB_RP_CASE(0) MSB_RP_CASE(1) MSB_RP_CASE(2) MSB_RP_CASE(3) MSB_RP_CASE(4) MSB_RP_CASE(5)
         MSB_RP_CASE(6) MSB_RP_CASE(7) MSB_RP_CASE(8) MSB_RP_CASE(9) MSB_RP_CASE(10)
 #undef MSB_RP_CASE
+        default:
+            return set_error(MSB_ERR_ARG, "render_preprocess_fwd: unsupported degree");
     }
-    return set_error(MSB_ERR_ARG, "render_preprocess_fwd: unsupported degree");
+    if (rc) return rc;
+    if (total_dev) {  // M = sum(tiles) -> pinned host memory; the caller synchronises the stream before reading it
+        cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: cudaMemcpyAsync failed");
+    }
+    return MSB_OK;
 }
 
 // Fused backward.  grec [P,8] = {dL_duv.xy, dL_dconic.xyz, dL_dopacity, -, -} and gfeat [P,Cpad]

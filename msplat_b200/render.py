@@ -124,6 +124,7 @@ class _RenderSHViews(torch.autograd.Function):
         views = []
         with torch.cuda.device(dev):
             totals = _lib.pinned_i64(dev, B)
+            total_dev = torch.empty((B,), dtype=torch.int64, device=dev)
             # phase A: per-Gaussian preprocess + tile-count scan of every view, then ONE host sync
             for b in range(B):
                 rec = torch.empty((P, 8), dtype=f32, device=dev)
@@ -132,13 +133,11 @@ class _RenderSHViews(torch.autograd.Function):
                 depth = torch.empty((P,), dtype=f32, device=dev)
                 radius = torch.empty((P,), dtype=i32, device=dev)
                 tiles = torch.empty((P,), dtype=i32, device=dev)
+                # M = sum(tiles) is accumulated by the same kernel and copied to the pinned totals[b]
                 _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd, dev, ptr(x), ptr(s),
                           ptr(q), ptr(o), ptr(sh), ptr(I[b]), ptr(E[b]), P, Cs, D, int(with_depth), W, H, nearest,
                           extent, sh_bias, int(clamp), ptr(rec), ptr(featp), ptr(uv), ptr(depth), ptr(radius),
-                          ptr(tiles))
-                ws1 = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
-                _lib.call("sort_scan", 2 if P else 0, L.msb_sort_scan, dev, ptr(tiles), P, None,
-                          ptr(totals[b:]), ptr(ws1), ws1.numel())
+                          ptr(tiles), ptr(total_dev[b:]), ptr(totals[b:]))
                 views.append([rec, featp, uv, depth, radius, tiles])
             main = torch.cuda.current_stream(dev)
             main.synchronize()
