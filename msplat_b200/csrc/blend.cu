@@ -520,10 +520,12 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
     return check_launch("alpha_blending_fwd");
 }
 
-// A/B switch for profiling runs (CH = 4).  Measured on BASELINE config #3 (profiles/r1_ab_blend_bwd.md):
-//   default  256-entry batches, compiler's register count (80 -> 3 CTAs/SM)   1.064 ms
-//   1        128-entry batches, 80 registers (3 CTAs/SM)                      1.111 ms
-//   3        128-entry batches, 64 registers (4 CTAs/SM, 40 B of spills)      1.150 ms
+// A/B switch for profiling runs (CH = 4), MSB_BWD_CFG.  Measured on BASELINE config #3
+// (profiles/r1_ab_experiments.md):
+//   default  256-entry batches, registers capped for 3 CTAs/SM (80)            1.054 ms
+//   1        128-entry batches, 3 CTAs/SM                                       1.11 ms
+//   2        256-entry batches, uncapped (93 registers -> 2 CTAs/SM)            1.19 ms
+//   3        128-entry batches, 64 registers (4 CTAs/SM, spills)                1.15 ms
 // Fewer barriers per list entry beat the extra resident CTA.
 static int blend_bwd_cfg() {
     static const int v = [] { const char* e = getenv("MSB_BWD_CFG"); return e ? atoi(e) : 0; }();
