@@ -53,22 +53,35 @@ def _side_stream(dev) -> "torch.cuda.Stream":
 def rasterization_sh(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intr: Tensor, extr: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3,
-) -> Tensor:
+    nearest: float = 0.0, extent: float = 1.3, ndc: Tensor = None, return_aux: bool = False,
+):
     """One camera.  xyz [P,3], scale [P,3], rotate [P,4] (r,x,y,z; not normalised inside),
     opacity [P,1], shs [P,Cs,D] with D=(deg+1)^2, intr [4], extr [3,4]|[4,4] -> image [C,H,W],
-    C = Cs (+1 depth channel if ``with_depth``)."""
-    return rasterization_sh_views(xyz, scale, rotate, opacity, shs, intr[None], extr[None], W, H, bg, sh_bias=sh_bias,
-                                  clamp=clamp, with_depth=with_depth, nearest=nearest, extent=extent)[0]
+    C = Cs (+1 depth channel if ``with_depth``).  ``ndc`` [P,2] / ``return_aux``: see
+    :func:`rasterization_sh_views` (aux tensors come back without the view dimension)."""
+    out = rasterization_sh_views(xyz, scale, rotate, opacity, shs, intr[None], extr[None], W, H, bg, sh_bias=sh_bias,
+                                 clamp=clamp, with_depth=with_depth, nearest=nearest, extent=extent,
+                                 ndc=None if ndc is None else ndc[None], return_aux=return_aux)
+    if return_aux:
+        return out[0][0], out[1][0], out[2][0]
+    return out[0]
 
 
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3,
-) -> Tensor:
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3, ndc: Tensor = None,
+    return_aux: bool = False,
+):
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
     -> images [B,C,H,W].
+
+    Side outputs a 3DGS trainer reads every step, at no extra pass:
+    ``ndc`` [B,P,2] is a dummy input whose ``.grad`` receives the screen-space gradient
+    ``dL_duv * [0.5 W, 0.5 H]`` of every view (the reference's hook, msplat/alpha_blending.py:107-110,
+    which densification heuristics accumulate); ``return_aux=True`` returns
+    ``(images, radii [B,P] int32, visible [B,P] bool)`` with ``visible = radii > 0`` (the Gaussians
+    that take part in a view, src/sort_gaussian.cu:26).
 
     ``grad_sync`` (view-batch data parallelism): a ``torch.distributed`` process group
     (or ``True`` for the default group).  The backward pass then returns the per-Gaussian gradients
@@ -80,9 +93,14 @@ def rasterization_sh_views(
     object with ``.wait()``."""
     if intrs.dim() == 1:
         intrs = intrs[None].expand(extrs.shape[0], 4)
-    return _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
-                                float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent),
-                                grad_sync, int(grad_chunks))
+    if ndc is not None and tuple(ndc.shape) != (extrs.shape[0], xyz.shape[0], 2):
+        raise RuntimeError("rasterization_sh_views: ndc must be [B, P, 2]")
+    images, radii = _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
+                                         float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent),
+                                         grad_sync, int(grad_chunks), ndc, bool(return_aux))
+    if return_aux:
+        return images, radii, radii > 0
+    return images
 
 
 def _resolve_group(grad_sync):
@@ -99,7 +117,7 @@ def _resolve_group(grad_sync):
 class _RenderSHViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scale, rotate, opacity, shs, intrs, extrs, W, H, bg, sh_bias, clamp, with_depth, nearest,
-                extent, grad_sync, grad_chunks):
+                extent, grad_sync, grad_chunks, ndc, return_aux):
         x, s, q = as_f32(xyz, "xyz"), as_f32(scale, "scale"), as_f32(rotate, "rotate")
         o, sh = as_f32(opacity, "opacity"), as_f32(shs, "shs")
         I, E = as_f32(intrs, "intrs"), as_f32(extrs, "extrs")
@@ -145,6 +163,7 @@ class _RenderSHViews(torch.autograd.Function):
             side = _side_stream(dev) if (OVERLAP and B > 1) else None
             # phase B: sort (side stream when overlapping) + blend (caller's stream) per view
             saved, keep = [], []
+            radii = torch.stack([v[4] for v in views]) if return_aux else torch.empty((0,), dtype=i32, device=dev)
             for b in range(B):
                 rec, featp, uv, depth, radius, tiles = views[b]
                 M = Ms[b]
@@ -172,11 +191,13 @@ class _RenderSHViews(torch.autograd.Function):
         ctx.cam_grad = (intrs.requires_grad, extrs.requires_grad)
         ctx.grad_sync = (grad_sync, grad_chunks)
         ctx.shapes = (tuple(opacity.shape), tuple(intrs.shape), tuple(extrs.shape))
+        ctx.has_ndc = ndc is not None
         ctx.save_for_backward(x, s, q, sh, I, E, *saved)
-        return images
+        ctx.mark_non_differentiable(radii)
+        return images, radii
 
     @staticmethod
-    def backward(ctx, dL_dimages):
+    def backward(ctx, dL_dimages, _dL_dradii=None):
         B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth = ctx.cfg
         x, s, q, sh, I, E = ctx.saved_tensors[:6]
         saved = ctx.saved_tensors[6:]
@@ -190,6 +211,9 @@ class _RenderSHViews(torch.autograd.Function):
         dop = torch.empty((P,), dtype=f32, device=dev)
         dshs = torch.empty_like(sh)
         need_i, need_e = ctx.cam_grad
+        # screen-space gradient hook: dL_duv of view b is columns 0:2 of its packed gradient record
+        dndc = torch.zeros((B, P, 2), dtype=f32, device=dev) if ctx.has_ndc else None
+        ndc_scale = torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev) if ctx.has_ndc else None
         dintr = torch.zeros((B, 4), dtype=f32, device=dev) if need_i else None
         dextr = torch.zeros((B,) + tuple(E.shape[1:]), dtype=f32, device=dev) if need_e else None
         if P == 0 or C == 0:
@@ -223,6 +247,8 @@ class _RenderSHViews(torch.autograd.Function):
                     gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(B)]
                     for b in range(B):
                         blend_bwd(b, grec[b], gfeat[b])
+                        if dndc is not None:
+                            torch.mul(grec[b][:, :2], ndc_scale, out=dndc[b])
                     nchunk = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
                     step = ((P + nchunk - 1) // nchunk + 255) // 256 * 256  # slab starts stay 16-byte aligned
                     works = []
@@ -252,6 +278,8 @@ class _RenderSHViews(torch.autograd.Function):
                         if side is not None and b >= nbuf:
                             main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
                         blend_bwd(b, grec[k], gfeat[k])
+                        if dndc is not None:  # on `main`, before blend_bwd(b + nbuf) rewrites the buffer
+                            torch.mul(grec[k][:, :2], ndc_scale, out=dndc[b])
                         with torch.cuda.stream(side if side is not None else main):
                             if side is not None:
                                 side.wait_event(main.record_event())
@@ -262,7 +290,7 @@ class _RenderSHViews(torch.autograd.Function):
                         main.wait_stream(side)
         op_shape = ctx.shapes[0]
         return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr, dextr, None, None, None, None, None, None,
-                None, None, None, None)
+                None, None, None, None, dndc, None)
 
 
 def _blend_passes_fwd(cpad: int, C: int) -> int:

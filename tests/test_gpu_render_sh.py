@@ -228,3 +228,61 @@ def test_render_sh_edge_cases(ms):
         ms.rasterization_sh(*[a.detach() for a in A[:4]], torch.zeros(300, 3, 15, device=DEV), intr, extr, 64, 48, 0.0)
     with pytest.raises(RuntimeError, match="CUDA"):
         ms.rasterization_sh(*[a.detach().cpu() for a in A], intr, extr, 64, 48, 0.0)
+
+
+def test_render_sh_ndc_hook_and_aux(ms):
+    """the screen-space gradient hook (``ndc``) and the radii / visibility side
+    outputs of the fused path equal what the steps API gives view by view
+    (msplat/alpha_blending.py:107-110 hook, ewa_project radius), also under the slab schedule."""
+    P, W, H, bg, deg, Cs, nv = 9000, 240, 160, 0.0, 2, 3, 3
+    intr, extr = camera(W, H)
+    extrs = []
+    for k in range(nv):
+        e = extr.clone()
+        e[0, 3] += 0.25 * (k - 1)
+        extrs.append(e)
+    extrs = torch.stack(extrs).to(DEV)
+    intrs = intr.to(DEV)[None].repeat(nv, 1)
+    g = torch.randn(nv, Cs + 1, H, W, generator=torch.Generator().manual_seed(4)).to(DEV)
+
+    # steps API, one view at a time
+    S = make_leaves(P, Cs, deg, 90, DEV)
+    ndc_s, radii_s = [], []
+    for k in range(nv):
+        xyz, scale, quat, opacity, shs = S
+        uv, depth = ms.project_point(xyz, intrs[k], extrs[k], W, H)
+        vis = depth != 0
+        dirs = xyz - cam_center(extrs[k])
+        dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+        rgb = torch.clamp_min(ms.compute_sh(shs, dirs, vis.squeeze(-1)) + 0.5, 0.0)
+        feat = torch.cat([rgb, depth], dim=-1)
+        cov = ms.compute_cov3d(scale, quat, vis)
+        conic, radius, tiles = ms.ewa_project(xyz, cov, intrs[k], extrs[k], uv, W, H, vis)
+        ids, tr = ms.sort_gaussian(uv, depth, W, H, radius, tiles)
+        ndc = torch.zeros(P, 2, device=DEV, requires_grad=True)
+        img = ms.alpha_blending(uv, conic, opacity, feat, ids, tr, bg, W, H, ndc)
+        (img * g[k]).sum().backward()
+        ndc_s.append(ndc.grad)
+        radii_s.append(radius)
+
+    for sync in (None, lambda t: None):  # plain schedule and the slab schedule of the data-parallel path
+        F = make_leaves(P, Cs, deg, 90, DEV)
+        ndc = torch.zeros(nv, P, 2, device=DEV, requires_grad=True)
+        imgs, radii, visible = ms.rasterization_sh_views(*F, intrs, extrs, W, H, bg, with_depth=True, ndc=ndc,
+                                                         return_aux=True, grad_sync=sync)
+        assert radii.dtype == torch.int32 and radii.shape == (nv, P) and visible.dtype == torch.bool
+        assert not radii.requires_grad
+        (imgs * g).sum().backward()
+        for k in range(nv):
+            assert torch.equal(radii[k], radii_s[k]), f"view {k}: radii differ from ewa_project"
+            assert torch.equal(visible[k], radii_s[k] > 0)
+            grad_close(ndc.grad[k], ndc_s[k], rel=2e-3, eps=2e-4, what=f"view {k} ndc hook")
+        for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], F, S):
+            grad_close(a.grad, b.grad, rel=2e-3, eps=2e-4, what=f"aux run d{n}")
+    # single-view wrapper
+    F = make_leaves(P, Cs, deg, 90, DEV)
+    ndc1 = torch.zeros(P, 2, device=DEV, requires_grad=True)
+    img, rad, vis = ms.rasterization_sh(*F, intrs[0], extrs[0], W, H, bg, with_depth=True, ndc=ndc1, return_aux=True)
+    (img * g[0]).sum().backward()
+    assert torch.equal(rad, radii_s[0]) and torch.equal(vis, radii_s[0] > 0)
+    grad_close(ndc1.grad, ndc_s[0], rel=2e-3, eps=2e-4, what="single-view ndc hook")
