@@ -120,9 +120,11 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
     // full blocks: the four input slabs arrive as TMA bulk copies issued by one thread (3 + 3 + 4 + 1 KB
     // at G = 256), everyone waits on the mbarrier; the ragged last block uses the per-thread path
     __shared__ unsigned long long s_bar;
+    __shared__ unsigned int s_tsum;
     const bool full = rows == G;
     if (tid == 0) {
         s_cnt = 0;
+        s_tsum = 0;
         if (full) mbar_init(&s_bar, 1);
     }
     __syncthreads();
@@ -172,9 +174,10 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
         unsigned wsum = (unsigned)til;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        if ((tid & 31) == 0 && wsum) atomicAdd(total_tiles, (unsigned long long)wsum);
+        if ((tid & 31) == 0 && wsum) atomicAdd(&s_tsum, wsum);
     }
     __syncthreads();  // every thread is done with the input slabs
+    if (total_tiles != nullptr && tid == 0 && s_tsum) atomicAdd(total_tiles, (unsigned long long)s_tsum);  // one per CTA
     if (t < rows) {
         float4* r = reinterpret_cast<float4*>(sm) + 2 * t;
         r[0] = make_float4(u, v, cx, cy);
