@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Tuple
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -39,15 +41,18 @@ OVERLAP = True
 _side_streams = {}
 
 
-def _side_stream(dev) -> "torch.cuda.Stream":
+SORT_STREAMS = int(os.environ.get("MSB_SORT_STREAMS", "1"))  # side streams the sorts of a view batch rotate over
+
+
+def _side_stream(dev, k: int = 0) -> "torch.cuda.Stream":
     idx = torch.device(dev).index
     if idx is None:
         idx = torch.cuda.current_device()
-    if idx not in _side_streams:
+    if (idx, k) not in _side_streams:
         # high priority: its CTAs are dispatched as soon as blend CTAs retire instead of queueing behind the
         # thousands of tile CTAs of the blend kernel launched before them
-        _side_streams[idx] = torch.cuda.Stream(device=idx, priority=-1)
-    return _side_streams[idx]
+        _side_streams[(idx, k)] = torch.cuda.Stream(device=idx, priority=-1)
+    return _side_streams[(idx, k)]
 
 
 def rasterization_sh(
@@ -160,7 +165,10 @@ class _RenderSHViews(torch.autograd.Function):
             main = torch.cuda.current_stream(dev)
             main.synchronize()
             Ms = [int(totals[b]) for b in range(B)]
-            side = _side_stream(dev) if (OVERLAP and B > 1) else None
+            sides = [_side_stream(dev, k) for k in range(max(1, SORT_STREAMS))] if (OVERLAP and B > 1) else None
+            if sides is not None:
+                for st_ in sides[1:]:
+                    st_.wait_stream(main)  # the per-view tensors were produced on `main`
             # phase B: sort (side stream when overlapping) + blend (caller's stream) per view
             saved, keep = [], []
             radii = torch.stack([v[4] for v in views]) if return_aux else torch.empty((0,), dtype=i32, device=dev)
@@ -175,6 +183,7 @@ class _RenderSHViews(torch.autograd.Function):
                 final_T = torch.empty((H, W), dtype=f32, device=dev)
                 ncontrib = torch.empty((H, W), dtype=i32, device=dev)
                 nk = 4 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0  # keygen, offsets, duplicate, ranges + passes
+                side = sides[b % len(sides)] if sides is not None else None
                 with torch.cuda.stream(side if side is not None else main):
                     _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius),
                               ptr(tiles), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
