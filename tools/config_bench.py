@@ -136,6 +136,18 @@ def config2():
         _, radius, tiles = ms.ewa_project(sc.xyz, cov, sc.intr, sc.extr, uv, 512, 512, depth != 0)
         out["keys"] = int(tiles.sum())
     out["ms_fwd_bwd"] = {"msplat_b200 rasterization()": round(timed(lambda: run(ms)), 3)}
+    # per-C-ABI-call durations of one fwd+bwd (CUDA events on the launching stream)
+    from msplat_b200 import _lib
+    _lib.TIMING = []
+    run(ms)
+    torch.cuda.synchronize()
+    tl, _lib.TIMING = _lib.TIMING, None
+    stages = {}
+    for name, a, b in tl:
+        stages[name] = round(stages.get(name, 0.0) + a.elapsed_time(b), 4)
+    out["stage_ms"] = stages
+    if "sort_gaussian" in stages:
+        out["sort_Gkeys_per_s"] = round(out["keys"] / (stages["sort_gaussian"] * 1e-3) / 1e9, 1)
     if ref is not None:
         out["image_max_abs_err"] = float((run(ms).detach() - run(ref).detach()).abs().max())
         out["ms_fwd_bwd"]["reference build rasterization()"] = round(timed(lambda: run(ref)), 3)
