@@ -592,7 +592,7 @@ __device__ __forceinline__ void peer_bit(unsigned d, unsigned& m) {
 // at about the same time and the full prefixes then advance LB tiles per round trip while each
 // waiting tile walks back LB per round trip: tile k resolves after ~k / (2 LB) round trips, so
 // those passes want a wide window; the multi-wave tile passes resolve within the first window.
-// IPT: keys per thread (16).  A/B on BASELINE config #3 (profiles/r1_ab_sort.md): 8 keys per thread
+// IPT: keys per thread (16).  A/B on BASELINE config #3 (profiles/r1_ab_experiments.md): 8 keys per thread
 // at 6 CTAs/SM and look-back windows of 16 / 32 were not faster for the L2-resident depth passes;
 // what helped them was the single-lane wait below (gate_ns).
 template <bool DEVN, int LB, int NB, int IPT>
