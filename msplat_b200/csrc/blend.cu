@@ -560,7 +560,9 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float
             default: return launch_bwd_cfg<CH, 256, 3>(MSB_BWD_ARGS);
         }
     } else {
-        return launch_bwd_cfg<CH, 256, 0>(MSB_BWD_ARGS);
+        // CH = 16: registers capped at 128 so that two CTAs fit an SM (143 uncapped -> one); CH = 8 is limited to
+        // two CTAs by shared memory either way
+        return launch_bwd_cfg<CH, 256, (CH == 16 ? 2 : 0)>(MSB_BWD_ARGS);
     }
 #undef MSB_BWD_ARGS
 }

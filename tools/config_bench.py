@@ -108,6 +108,17 @@ def sh_config(name, Pn, W, H, sigma, deg, Cs, with_depth, extr=None):
         img = ms.rasterization_sh(*P, sc.intr, extr, W, H, 0.0, with_depth=with_depth)
         (img * G).sum().backward()
 
+    from msplat_b200 import _lib
+    run_fused()
+    torch.cuda.synchronize()
+    _lib.TIMING = []
+    run_fused()
+    torch.cuda.synchronize()
+    tl, _lib.TIMING = _lib.TIMING, None
+    stages = {}
+    for nm, a, b in tl:
+        stages[nm] = round(stages.get(nm, 0.0) + a.elapsed_time(b), 4)
+    out["fused_stage_ms"] = stages
     out["ms_fwd_bwd"] = {"msplat_b200 fused": round(timed(run_fused), 3),
                          "msplat_b200 steps API": round(timed(lambda: run_steps(ms)), 3)}
     if ref is not None:
