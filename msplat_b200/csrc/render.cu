@@ -304,6 +304,18 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     const Cam c = load_cam(intr, extr);
     const CamCenter cc = cam_center(c);
     __shared__ unsigned long long s_bar;
+    // write mode: the all-zero dL_dshs rows of Gaussians without a colour gradient are filled by bulk stores
+    // from this zero block (one instruction per 2 KB instead of a lane group walking the row)
+    // (compiled in for degree >= 5 only: for short rows the lane groups are as fast)
+    constexpr bool ZF = DEG >= 5;
+    constexpr int ZB = ZF ? 512 : 4;
+    __shared__ __align__(16) float s_zero[ZB];
+    const size_t row_bytes = (size_t)Cs * D * sizeof(float);
+    const bool zero_fill = ZF && !accumulate && (row_bytes % 16) == 0 && row_bytes >= 1024;
+    if constexpr (ZF) {
+        for (int i = tid; i < ZB; i += RP_NT) s_zero[i] = 0.f;
+        fence_async_smem();
+    }
     const bool full = rows == G;  // full blocks move their slabs with TMA bulk copies (see the forward kernel)
     if (tid == 0) {
         s_cnt = 0;
@@ -350,8 +362,16 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     }
     // write mode: every row of dL_dshs must be produced (zeros for untouched Gaussians);
     // accumulate mode: only rows that actually change are touched
-    const bool listed = accumulate ? live : (t < rows);
+    const bool listed = (accumulate || zero_fill) ? live : (t < rows);
     list_append(listed, (unsigned)t | (vis ? 0u : RP_INVISIBLE) | (live ? 0u : RP_DEAD), s_list, &s_cnt);
+    bool filled = false;
+    if (ZF && zero_fill && t < rows && !live) {
+        char* row = reinterpret_cast<char*>(dL_dshs) + (size_t)(g0 + t) * row_bytes;
+        for (size_t off = 0; off < row_bytes; off += ZB * sizeof(float))
+            bulk_s2g(row + off, s_zero, (unsigned)min((size_t)(ZB * sizeof(float)), row_bytes - off));
+        bulk_commit();
+        filled = true;
+    }
     __syncthreads();
 
     // ---- phase 2: dL_dshs rows + w_d = sum_c dL_dvalue_c * shs[c, d] ------------------------------
@@ -525,7 +545,7 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
         }
     }
     if (CAM) cam_reduce_atomic<RP_NT>(cam, dL_dintr, dL_dextr, s_red);
-    if (full && tid == 0) bulk_wait_read();  // shared memory stays valid until the copy engine has read it
+    if ((full && tid == 0) || filled) bulk_wait_read();  // shared memory stays valid until the copy engine has read it
 }
 
 static size_t rp_smem_fwd(int deg, int Cpad) {
