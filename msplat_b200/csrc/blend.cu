@@ -9,11 +9,11 @@
 //
 // Design (one CTA of 256 threads per 16x16 tile, like the reference, but):
 //  * a pack pass turns the per-Gaussian inputs into one 32-byte record
-//      {u, v, conic.x, conic.y | conic.z, opacity, hx, hy}
+//      {u, v, conic.x, conic.y | conic.z, opacity, fp16x2(hx, hy), fp16x2(hs, ht)}
 //    plus a 16-byte-aligned feature row, so a batch of 256 list entries is staged into shared
 //    memory with 16-byte cp.async (LDGSTS) copies, double-buffered against the blend loop;
 //  * each warp owns an 8x4 pixel block; lane l tests staged Gaussian 32k+l against the warp's
-//    block (conservative alpha-footprint box hx, hy, blend_math.cuh) and a ballot yields the
+//    block (conservative alpha-footprint octagon, blend_math.cuh) and a ballot yields the
 //    Gaussians worth visiting -- most of a tile's list never touches a given 8x4 block, so the
 //    per-pair work drops by ~3-4x without changing any pixel's result;
 //  * warp-vote early termination (a warp stops when its 32 pixels are done, the CTA when all are);
@@ -45,10 +45,11 @@ __global__ void __launch_bounds__(256) blend_pack_kernel(int P, int C, int Cpad,
     const float2 p = uv[i];
     const float cx = conic[3 * i], cy = conic[3 * i + 1], cz = conic[3 * i + 2];
     const float op = opacity[i];
-    float hx, hy;
-    cull_extent(cx, cy, cz, op, hx, hy);
+    float hx, hy, hs, ht, p0, p1;
+    cull_extent(cx, cy, cz, op, hx, hy, hs, ht);
+    cull_pack(hx, hy, hs, ht, p0, p1);
     rec[2 * i] = make_float4(p.x, p.y, cx, cy);
-    rec[2 * i + 1] = make_float4(cz, op, hx, hy);
+    rec[2 * i + 1] = make_float4(cz, op, p0, p1);
     if (featp != nullptr) {
         for (int k = 0; k < Cpad; ++k) featp[i * Cpad + k] = k < C ? feature[i * C + k] : 0.f;
     }
@@ -154,16 +155,14 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
             if (k0 + lane < cnt) {
                 const float4 r0 = st.rec[2 * (k0 + lane)];
                 const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
-                                  (r0.y - r1.w > wy1);
-                hit = !miss;
+                hit = !cull_miss(r0.x, r0.y, r1.z, r1.w, wx0, wy0, 8.0f, 4.0f);
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int j = k0 + __ffs(m) - 1;
                 m &= m - 1;
                 const float4 r0 = st.rec[2 * j];      // u, v, cx, cy   (broadcast LDS.128)
-                const float4 r1 = st.rec[2 * j + 1];  // cz, opacity, hx, hy
+                const float4 r1 = st.rec[2 * j + 1];  // cz, opacity, packed cull extents
                 const float dx = fadd(r0.x, -pxf), dy = fadd(r0.y, -pyf);
                 const float power = pair_power(dx, dy, r0.z, r0.w, r1.x);
                 const float G = ex2_approx(fmul(power, kLog2e));
@@ -425,9 +424,7 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
             if (k0 + lane < bcnt) {
                 const float4 r0 = st.rec[2 * (k0 + lane)];
                 const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                const bool miss = (r0.x + r1.z < wx0) || (r0.x - r1.z > wx1) || (r0.y + r1.w < wy0) ||
-                                  (r0.y - r1.w > wy1);
-                hit = !miss && (pos0 - (k0 + lane) < wmax);
+                hit = !cull_miss(r0.x, r0.y, r1.z, r1.w, wx0, wy0, 8.0f, 4.0f) && (pos0 - (k0 + lane) < wmax);
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             // alpha of a pair (alpha_blending.cu:190-203); the pos < lc test is :185-187

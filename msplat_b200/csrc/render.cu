@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
         }
         op = s_op[t];
         if (til > 0) {
-            cull_extent(cx, cy, cz, op, hx, hy);
+            float ex, ey, es, et;
+            cull_extent(cx, cy, cz, op, ex, ey, es, et);
+            cull_pack(ex, ey, es, et, hx, hy);  // hx, hy now hold the packed FP16 pairs of the blend record
             const float rx = px - cc.x, ry = py - cc.y, rz = pz - cc.z;
             const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
             sh_basis<DEG>(rx * inv, ry * inv, rz * inv, s_B + t, GS);

@@ -159,14 +159,27 @@ def test_blend_pair_math_and_cull_extent(host_check):
     np.testing.assert_allclose(F, img[:, 5, 7].numpy(), rtol=1e-5, atol=1e-6)
     assert abs(Tf - float(fT[5, 7])) < 1e-6 and last.value == int(nc[5, 7])
     # culling extents are conservative
-    hxy = np.zeros((n, 2), np.float32)
-    host_check.hc_cull_extent(n, fp(conic), fp(op), fp(hxy))
+    ext = np.zeros((n, 4), np.float32)  # hx, hy, hs (|dx + dy|), ht (|dx - dy|) after the FP16 round trip
+    host_check.hc_cull_extent(n, fp(conic), fp(op), fp(ext))
     ys, xs = np.mgrid[0:16, 0:16]
+    culled_blocks = 0
     for j in range(n):
         dx, dy = uv[j, 0] - xs, uv[j, 1] - ys
         power = -0.5 * (conic[j, 0] * dx * dx + conic[j, 2] * dy * dy) - conic[j, 1] * dx * dy
         alpha = np.minimum(0.99, op[j] * np.exp(power))
         passes = (power <= 0) & (alpha >= 1.0 / 255.0)
         if passes.any():
-            assert (np.abs(dx[passes]) <= hxy[j, 0]).all() and (np.abs(dy[passes]) <= hxy[j, 1]).all(), j
-    assert (hxy[:20] < 0).all()  # opacity < 1/255 can never contribute
+            assert (np.abs(dx[passes]) <= ext[j, 0]).all() and (np.abs(dy[passes]) <= ext[j, 1]).all(), j
+            assert (np.abs(dx[passes] + dy[passes]) <= ext[j, 2]).all(), j
+            assert (np.abs(dx[passes] - dy[passes]) <= ext[j, 3]).all(), j
+        # the kernels' block test never rejects an 8x4 block that holds a passing pixel
+        for by in range(0, 16, 4):
+            for bx in range(0, 16, 8):
+                miss = host_check.hc_cull_miss(ctypes.c_float(uv[j, 0]), ctypes.c_float(uv[j, 1]), fp(conic[j]),
+                                               ctypes.c_float(op[j]), ctypes.c_float(bx), ctypes.c_float(by),
+                                               ctypes.c_float(8.0), ctypes.c_float(4.0))
+                if miss:
+                    culled_blocks += 1
+                    assert not passes[by:by + 4, bx:bx + 8].any(), (j, bx, by)
+    assert culled_blocks > 0
+    assert (ext[:20] < 0).all()  # opacity < 1/255 can never contribute

@@ -32,7 +32,11 @@ def cull_extent(cx, cy, cz, op):
     dead = op * 255.0 * 1.001 < 1.0
     hx[dead] = -np.inf
     hy[dead] = -np.inf
-    return hx, hy
+    hs = np.sqrt(np.maximum(k * (cx + cz - 2 * cy), 0)) * 1.0001 + 0.02  # half extent of x + y
+    ht = np.sqrt(np.maximum(k * (cx + cz + 2 * cy), 0)) * 1.0001 + 0.02  # half extent of x - y
+    hs[dead] = -np.inf
+    ht[dead] = -np.inf
+    return hx, hy, hs, ht
 
 
 def main():
@@ -49,7 +53,7 @@ def main():
     feat = torch.rand(P, 3)
     _, final_T, ncontrib, _ = oracle.alpha_blending_forward(uv, conic, sc.opacity, feat, ids, tr, 0.0, W, H)
     uvn, cn, opn = uv.numpy(), conic.numpy(), sc.opacity.numpy().reshape(-1)
-    hx, hy = cull_extent(cn[:, 0], cn[:, 1], cn[:, 2], opn)
+    hx, hy, hs, ht = cull_extent(cn[:, 0], cn[:, 1], cn[:, 2], opn)
     ids, tr, nc = ids.numpy(), tr.numpy(), ncontrib.numpy()
     gx, gy = W // 16, H // 16
     print(f"P={P} {W}x{H} M={ids.size} pairs={int(nc.sum())}")
@@ -57,6 +61,7 @@ def main():
     # unit shapes: name -> (units per warp, list of (x0, y0, w, h) relative to the warp's 8x4 block)
     shapes = {
         "warp 8x4": [(0, 0, 8, 4)],
+        "warp 8x4 octagon": [(0, 0, 8, 4)],
         "half 4x4": [(0, 0, 4, 4), (4, 0, 4, 4)],
         "half 8x2": [(0, 0, 8, 2), (0, 2, 8, 2)],
         "quarter 4x2": [(0, 0, 4, 2), (4, 0, 4, 2), (0, 2, 4, 2), (4, 2, 4, 2)],
@@ -73,7 +78,7 @@ def main():
             if n <= 0:
                 continue
             g = ids[a:b]
-            u, v, ex, ey = uvn[g, 0], uvn[g, 1], hx[g], hy[g]
+            u, v, ex, ey, es, et = uvn[g, 0], uvn[g, 1], hx[g], hy[g], hs[g], ht[g]
             pos = np.arange(n)
             tile_nc = nc[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16]
             maxc = int(tile_nc.max())
@@ -89,6 +94,9 @@ def main():
                         Y0, Y1 = by0 + y0, by0 + y0 + uh - 1
                         umax = int(nc[Y0:Y1 + 1, X0:X1 + 1].max())
                         miss = (u + ex < X0) | (u - ex > X1) | (v + ey < Y0) | (v - ey > Y1)
+                        if "octagon" in name:
+                            sc_, tc_ = u + v, u - v
+                            miss = miss | (sc_ + es < X0 + Y0) | (sc_ - es > X1 + Y1) | (tc_ + et < X0 - Y1) | (tc_ - et > X1 - Y0)
                         hits.append((~miss) & (pos < umax))
                     hm = np.stack(hits, 0)  # [units, n]
                     sel = rpos >= 0

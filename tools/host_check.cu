@@ -145,8 +145,21 @@ float hc_blend_pixel(int n, const float* uv, const float* conic, const float* op
     return T;
 }
 
-void hc_cull_extent(int P, const float* conic, const float* opacity, float* hxy) {
-    for (int i = 0; i < P; ++i) cull_extent(conic[3 * i], conic[3 * i + 1], conic[3 * i + 2], opacity[i], hxy[2 * i], hxy[2 * i + 1]);
+// extents after the FP16 round trip of the blend record: out [P,4] = hx, hy, hs, ht
+void hc_cull_extent(int P, const float* conic, const float* opacity, float* out) {
+    for (int i = 0; i < P; ++i) {
+        float hx, hy, hs, ht, p0, p1;
+        cull_extent(conic[3 * i], conic[3 * i + 1], conic[3 * i + 2], opacity[i], hx, hy, hs, ht);
+        cull_pack(hx, hy, hs, ht, p0, p1);
+        cull_unpack(p0, p1, out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+    }
+}
+// block test used by the blend kernels
+int hc_cull_miss(float u, float v, const float* conic, float opacity, float x0, float y0, float w, float h) {
+    float hx, hy, hs, ht, p0, p1;
+    cull_extent(conic[0], conic[1], conic[2], opacity, hx, hy, hs, ht);
+    cull_pack(hx, hy, hs, ht, p0, p1);
+    return cull_miss(u, v, p0, p1, x0, y0, w, h) ? 1 : 0;
 }
 
 }  // extern "C"
