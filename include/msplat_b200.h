@@ -141,9 +141,10 @@ int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* id
  * feature = cat(colour, depth)) -- and the matching *Backward functions.  The camera centre is
  * -R^T t of extr.  shs [P,Cs,D], D = (deg+1)^2, deg <= 10.  C = Cs + (with_depth ? 1 : 0).
  * uv/depth/radius/tiles are bit-identical to msb_project_point_fwd / msb_ewa_project_fwd.
- * forward: total_dev (8 bytes of device scratch) and total_host (PINNED host memory) are optional
- * and go together: M = sum(tiles) is then accumulated by the kernel and copied asynchronously to
- * *total_host (synchronise the stream before reading it), which replaces msb_sort_scan here.
+ * forward: total_dev (8 bytes of device memory) and total_host (PINNED host memory) are optional:
+ * with total_dev, M = sum(tiles) is accumulated by the kernel into *total_dev (zeroed first); with
+ * total_host it is also copied asynchronously to *total_host (synchronise the stream before reading
+ * it).  Replaces msb_sort_scan on this path.
  * backward: accumulate != 0 adds into the outputs (view batches), else every element is written;
  * dL_dintr [4] / dL_dextr [12] may be NULL, otherwise they are accumulated into. */
 int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* opacity,

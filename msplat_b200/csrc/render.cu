@@ -628,14 +628,16 @@ int msb_blend_cpad(int C);
 // Fused forward preprocess of the SH render path.  Outputs: rec [P,8] and featp [P,Cpad]
 // (Cpad = msb_blend_cpad(Cs + with_depth)) in the blend kernels' packed layout, uv [P,2],
 // depth [P], radius [P], tiles [P] (bit-identical to project_point / ewa_project).  total_dev (8 bytes of
-// device scratch) / total_host (pinned) are optional: when given, M = sum(tiles) is accumulated by the kernel
-// and copied asynchronously to *total_host, which replaces msb_sort_scan for this path.
+// device memory) / total_host (pinned) are optional: with total_dev, M = sum(tiles) is accumulated by the kernel
+// into *total_dev (zeroed first); with total_host it is also copied asynchronously to *total_host (a view batch
+// leaves that out and copies all its totals at once).  Replaces msb_sort_scan for this path.
 int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float* quat, const float* opacity,
                               const float* shs, const float* intr, const float* extr, int P, int Cs, int D,
                               int with_depth, int W, int H, float nearest, float extent, float sh_bias, int clamp,
                               float* rec, float* featp, float* uv, float* depth, int32_t* radius, int32_t* tiles,
                               long long* total_dev, long long* total_host, void* stream) {
     if (P == 0) {
+        if (total_dev) cudaMemsetAsync(total_dev, 0, sizeof(long long), (cudaStream_t)stream);
         if (total_host) *total_host = 0;
         return MSB_OK;
     }
@@ -652,8 +654,8 @@ int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float*
                 intr, extr, W, H, nearest, extent, sh_bias, clamp ? 1 : 0, rec, featp, uv, depth, radius, tiles,
                 reinterpret_cast<unsigned long long*>(total_dev)};
     cudaStream_t st = (cudaStream_t)stream;
-    if ((total_dev == nullptr) != (total_host == nullptr))
-        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: total_dev and total_host go together");
+    if (total_host != nullptr && total_dev == nullptr)
+        return set_error(MSB_ERR_ARG, "render_preprocess_fwd: total_host needs total_dev");
     if (total_dev) {
         cudaError_t e = cudaMemsetAsync(total_dev, 0, sizeof(long long), st);
         if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: memset failed");
@@ -671,7 +673,7 @@ int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float*
             return set_error(MSB_ERR_ARG, "render_preprocess_fwd: unsupported degree");
     }
     if (rc) return rc;
-    if (total_dev) {  // M = sum(tiles) -> pinned host memory; the caller synchronises the stream before reading it
+    if (total_host) {  // M = sum(tiles) -> pinned host memory; the caller synchronises the stream before reading it
         cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: cudaMemcpyAsync failed");
     }

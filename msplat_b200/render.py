@@ -156,12 +156,13 @@ class _RenderSHViews(torch.autograd.Function):
                 depth = torch.empty((P,), dtype=f32, device=dev)
                 radius = torch.empty((P,), dtype=i32, device=dev)
                 tiles = torch.empty((P,), dtype=i32, device=dev)
-                # M = sum(tiles) is accumulated by the same kernel and copied to the pinned totals[b]
+                # M = sum(tiles) of view b is accumulated by the same kernel into total_dev[b]
                 _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd, dev, ptr(x), ptr(s),
                           ptr(q), ptr(o), ptr(sh), ptr(I[b]), ptr(E[b]), P, Cs, D, int(with_depth), W, H, nearest,
                           extent, sh_bias, int(clamp), ptr(rec), ptr(featp), ptr(uv), ptr(depth), ptr(radius),
-                          ptr(tiles), ptr(total_dev[b:]), ptr(totals[b:]))
+                          ptr(tiles), ptr(total_dev[b:]), None)
                 views.append([rec, featp, uv, depth, radius, tiles])
+            totals[:B].copy_(total_dev, non_blocking=True)  # one device->host copy for the whole batch
             main = torch.cuda.current_stream(dev)
             main.synchronize()
             Ms = [int(totals[b]) for b in range(B)]
