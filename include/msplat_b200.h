@@ -130,7 +130,7 @@ int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* id
                          void* stream);
 int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
-                         const float* dL_dimage, float* grec, float* gfeat, void* stream);
+                         const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream);
 
 /* ---- fused SH render preprocess ------------------------------------------------------------
  * One forward / one backward kernel for the whole per-Gaussian part of an SH-coloured render:

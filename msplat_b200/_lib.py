@@ -53,7 +53,7 @@ def _declare(lib):
         "msb_alpha_blending_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P, P, P, P, SZ, V]),
         "msb_alpha_blending_bwd": (I, [P, P, P, F, I, I, I, I, P, P, P, P, P, P, P, P, P, SZ, V]),
         "msb_blend_packed_fwd": (I, [P, P, P, P, F, I, I, I, P, P, P, V]),
-        "msb_blend_packed_bwd": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, P, V]),
+        "msb_blend_packed_bwd": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, P, I, V]),
         "msb_render_preprocess_fwd": (I, [P] * 7 + [I, I, I, I, I, I, F, F, F, I] + [P] * 8 + [V]),
         "msb_render_preprocess_bwd": (I, [P] * 9 + [I, I, I, I, F, I, I] + [P] * 7 + [V]),
     }

@@ -728,16 +728,18 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
 // msb_render_preprocess_bwd.
 int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
-                         const float* dL_dimage, float* grec, float* gfeat, void* stream) {
+                         const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (P < 0 || C < 0 || W <= 0 || H <= 0) return set_error(MSB_ERR_ARG, "blend_packed_bwd: bad argument");
     if (P == 0) return MSB_OK;
     if (!rec || !featp || !tile_range || !final_T || !ncontrib || !grec || !gfeat || (C > 0 && !dL_dimage))
         return set_error(MSB_ERR_ARG, "blend_packed_bwd: null pointer");
     const int Cpad = msb_blend_cpad(C);
-    cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)P * 8 * sizeof(float), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(gfeat, 0, (size_t)P * Cpad * sizeof(float), st);
-    if (e != cudaSuccess) return set_error((int)e, "blend_packed_bwd: memset failed");
+    if (!already_zero) {  // the kernels accumulate with reductions: the packed gradients start from zero
+        cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)P * 8 * sizeof(float), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(gfeat, 0, (size_t)P * Cpad * sizeof(float), st);
+        if (e != cudaSuccess) return set_error((int)e, "blend_packed_bwd: memset failed");
+    }
     return run_bwd_passes(st, reinterpret_cast<const float4*>(rec), featp, Cpad, C, idx_sorted, tile_range, bg, W, H,
                           final_T, ncontrib, dL_dimage, grec, gfeat);
 }

@@ -241,11 +241,11 @@ class _RenderSHViews(torch.autograd.Function):
                           1 if b > 0 else 0, ptr(dxyz[lo:hi]), ptr(dscale[lo:hi]), ptr(dquat[lo:hi]), ptr(dop[lo:hi]),
                           ptr(dshs[lo:hi]), ptr(dintr[b]) if need_i else None, ptr(dextr[b]) if need_e else None)
 
-            def blend_bwd(b, gr, gf):
+            def blend_bwd(b, gr, gf, already_zero=False):
                 rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
                 _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
                           ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
-                          ptr(gr), ptr(gf))
+                          ptr(gr), ptr(gf), int(already_zero))
 
             with torch.cuda.device(dev):
                 main = torch.cuda.current_stream(dev)
@@ -287,7 +287,9 @@ class _RenderSHViews(torch.autograd.Function):
                         k = b % nbuf
                         if side is not None and b >= nbuf:
                             main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
-                        blend_bwd(b, grec[k], gfeat[k])
+                        # from the third view on the buffer was cleared on the side stream (below), under the
+                        # backward blend of the view before: the 144 MB memset leaves the critical path
+                        blend_bwd(b, grec[k], gfeat[k], already_zero=(side is not None and b >= nbuf))
                         if dndc is not None:  # on `main`, before blend_bwd(b + nbuf) rewrites the buffer
                             torch.mul(grec[k][:, :2], ndc_scale, out=dndc[b])
                         with torch.cuda.stream(side if side is not None else main):
@@ -295,6 +297,9 @@ class _RenderSHViews(torch.autograd.Function):
                                 side.wait_event(main.record_event())
                             pre_bwd(b, grec[k], gfeat[k], 0, P)
                             if side is not None:
+                                if b + nbuf < B:
+                                    grec[k].zero_()
+                                    gfeat[k].zero_()
                                 done[b] = side.record_event()
                     if side is not None:
                         main.wait_stream(side)
