@@ -255,8 +255,21 @@ class _RenderSHViews(torch.autograd.Function):
                     import torch.distributed as dist
                     grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(B)]
                     gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(B)]
+                    # the packed gradient buffers are cleared on the side stream, under the backward blends of
+                    # the views before (only the first blend waits for its clear)
+                    side = _side_stream(dev) if OVERLAP else None
+                    cleared = [None] * B
+                    if side is not None:
+                        side.wait_stream(main)
+                        with torch.cuda.stream(side):
+                            for b in range(B):
+                                grec[b].zero_()
+                                gfeat[b].zero_()
+                                cleared[b] = side.record_event()
                     for b in range(B):
-                        blend_bwd(b, grec[b], gfeat[b])
+                        if side is not None:
+                            main.wait_event(cleared[b])
+                        blend_bwd(b, grec[b], gfeat[b], already_zero=side is not None)
                         if dndc is not None:
                             torch.mul(grec[b][:, :2], ndc_scale, out=dndc[b])
                     nchunk = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
