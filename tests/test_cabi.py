@@ -67,3 +67,30 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"project_point_fwd" in L.msb_last_error()
     rc = L.msb_compute_sh_fwd(None, None, None, 5, 3, 17, None, None)
     assert rc == -1
+
+
+def test_binding_table_matches_header_prototypes():
+    """Every prototype of include/msplat_b200.h and its ctypes binding in _lib.py agree in arity and
+    in the kind of each parameter (pointer / int / float / size_t / long long): catches a signature that
+    changed on one side only -- a mismatch would otherwise only show up as garbage on the GPU."""
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "msplat_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|const char\*)\s+(msb_\w+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) >= 27
+    L = _lib.lib()
+
+    def kind(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        base = decl.rsplit(" ", 1)[0].strip()
+        return {"int": "int", "float": "float", "size_t": "size_t", "long long": "ll"}[base]
+
+    ckind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "size_t",
+             ctypes.c_longlong: "ll"}
+    for name, params in protos:
+        params = params.strip()
+        want = [] if params in ("", "void") else [kind(p) for p in params.split(",")]
+        got = [ckind[a] for a in getattr(L, name).argtypes]
+        assert got == want, f"{name}: header {want} vs _lib.py {got}"
