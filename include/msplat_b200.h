@@ -122,9 +122,11 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
 
 /* ---- packed blend (inputs/gradients stay in the blend kernels' packed layout) --------------
  * Same kernels as msb_alpha_blending_fwd/bwd (src/alpha_blending.cu:248-573) without the
- * pack / unpack passes: rec [P,8] = {u, v, conic.x, conic.y | conic.z, opacity, hx, hy},
+ * pack / unpack passes: rec [P,8] = {u, v, conic.x, conic.y | conic.z, opacity, c0, c1} where c0, c1
+ * hold four FP16 culling extents (written by msb_render_preprocess_fwd; csrc/blend_math.cuh),
  * featp [P,Cpad], Cpad = msb_blend_cpad(C); grec [P,8] = {dL_duv.xy, dL_dconic.xyz,
- * dL_dopacity, 0, 0} and gfeat [P,Cpad] are zeroed and then accumulated by the backward call. */
+ * dL_dopacity, 0, 0} and gfeat [P,Cpad] are zeroed and then accumulated by the backward call;
+ * already_zero != 0 skips the zeroing (the caller cleared both buffers, e.g. on another stream). */
 int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
                          void* stream);
