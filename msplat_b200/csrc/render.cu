@@ -14,13 +14,15 @@
 // conic, radius and tiles are bit-identical to the steps API and to the reference build.
 //
 // Layout / roofline (HBM-bound): a block owns G consecutive Gaussians (G = 256 for degree <= 4).
-//   phase 1  one thread per Gaussian: [G,K] input slabs staged with coalesced 16-byte loads,
-//            geometry + cull extents + SH basis (once per Gaussian, into shared memory [D][G+1]);
-//            Gaussians that touch no tile are dropped here: their SH rows are never read;
+//   phase 1  one thread per Gaussian: [G,K] input slabs arrive as TMA bulk copies (cp.async.bulk +
+//            mbarrier; per-thread 16-byte loads for the ragged last block), geometry + packed cull extents
+//            + SH basis (once per Gaussian, into shared memory [D][G+1]); Gaussians that touch no tile
+//            are dropped here: their SH rows are never read; the forward also sums the tile counts (M);
 //   phase 2  groups of LPR lanes stream the surviving Gaussians' [Cs, D] coefficient rows with
 //            16-byte loads (sh_layout.cuh), shuffle-reduce, write colours into a shared slab;
 //   phase 3  (backward) one thread per Gaussian: dL_ddir -> dL_dxyz through the normalisation,
-//            projection / EWA / cov3d backward; outputs leave through shared slabs, 16-byte stores.
+//            projection / EWA / cov3d backward; outputs leave through shared slabs as bulk stores, or as
+//            bulk FP32 reduce-adds (cp.reduce.async.bulk) / red.global.v4 when accumulating over a view batch.
 // Algorithmic bytes per Gaussian at SH3 RGB+depth: forward 44 + 192*v in, 64 out;
 // backward 44 + 48 + 4 + 192*v in, 48 + 192 out (+ the same again when accumulating),
 // v = fraction of Gaussians that touch a tile.
