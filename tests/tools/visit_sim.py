@@ -62,6 +62,7 @@ def main():
     shapes = {
         "warp 8x4": [(0, 0, 8, 4)],
         "warp 8x4 octagon": [(0, 0, 8, 4)],
+        "warp 8x4 exact ellipse": [(0, 0, 8, 4)],
         "half 4x4": [(0, 0, 4, 4), (4, 0, 4, 4)],
         "half 8x2": [(0, 0, 8, 2), (0, 2, 8, 2)],
         "quarter 4x2": [(0, 0, 4, 2), (4, 0, 4, 2), (0, 2, 4, 2), (4, 2, 4, 2)],
@@ -79,6 +80,8 @@ def main():
                 continue
             g = ids[a:b]
             u, v, ex, ey, es, et = uvn[g, 0], uvn[g, 1], hx[g], hy[g], hs[g], ht[g]
+            qa, qb, qc = cn[g, 0], cn[g, 1], cn[g, 2]
+            tau = 2.0 * np.log(np.maximum(opn[g] * 255.0, 1e-30)) * 1.001 + 0.05
             pos = np.arange(n)
             tile_nc = nc[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16]
             maxc = int(tile_nc.max())
@@ -94,6 +97,15 @@ def main():
                         Y0, Y1 = by0 + y0, by0 + y0 + uh - 1
                         umax = int(nc[Y0:Y1 + 1, X0:X1 + 1].max())
                         miss = (u + ex < X0) | (u - ex > X1) | (v + ey < Y0) | (v - ey > Y1)
+                        if "exact" in name:
+                            # min of q over the block: nearest point candidates on the two facing edges
+                            ax0, ax1, ay0, ay1 = u - X1, u - X0, v - Y1, v - Y0
+                            xe, ye = np.clip(0.0, ax0, ax1), np.clip(0.0, ay0, ay1)
+                            ya = np.clip(-qb * xe / qc, ay0, ay1)
+                            xb = np.clip(-qb * ye / qa, ax0, ax1)
+                            q1 = qa * xe * xe + 2 * qb * xe * ya + qc * ya * ya
+                            q2 = qa * xb * xb + 2 * qb * xb * ye + qc * ye * ye
+                            miss = miss | (np.minimum(q1, q2) > tau)
                         if "octagon" in name:
                             sc_, tc_ = u + v, u - v
                             miss = miss | (sc_ + es < X0 + Y0) | (sc_ - es > X1 + Y1) | (tc_ + et < X0 - Y1) | (tc_ - et > X1 - Y0)
