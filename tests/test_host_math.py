@@ -183,3 +183,18 @@ def test_blend_pair_math_and_cull_extent(host_check):
                     assert not passes[by:by + 4, bx:bx + 8].any(), (j, bx, by)
     assert culled_blocks > 0
     assert (ext[:20] < 0).all()  # opacity < 1/255 can never contribute
+
+
+def test_cull_extent_fp16_packing_rounds_up(host_check):
+    """The culling extents travel as FP16: the round trip never shrinks a value (an extent that
+    became smaller could cull a contributing pair), overflows become +inf (= no culling)."""
+    rng = np.random.default_rng(9)
+    vals = np.concatenate([np.exp(rng.uniform(np.log(1e-4), np.log(6e4), 4000)),
+                           [0.0, 1e-8, 65504.0, 65505.0, 7e4, 1e9, np.inf, -np.inf]]).astype(np.float32)
+    vals = np.resize(vals, (len(vals) + 3) // 4 * 4)
+    out = np.zeros_like(vals)
+    host_check.hc_cull_pack_roundtrip(len(vals) // 4, fp(vals), fp(out))
+    assert (out >= vals).all()
+    fin = np.isfinite(vals) & (vals > 1e-3) & (vals < 6e4)
+    assert (out[fin] <= vals[fin] * (1 + 2.0 ** -10)).all()  # at most one FP16 ulp of slack
+    assert np.isposinf(out[vals > 65504.0]).all() and np.isneginf(out[np.isneginf(vals)]).all()

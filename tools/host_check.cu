@@ -154,6 +154,14 @@ void hc_cull_extent(int P, const float* conic, const float* opacity, float* out)
         cull_unpack(p0, p1, out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
     }
 }
+// FP16 round trip of four extents: out >= in must hold for every finite or infinite input
+void hc_cull_pack_roundtrip(int n, const float* in, float* out) {
+    for (int i = 0; i < n; ++i) {
+        float p0, p1;
+        cull_pack(in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3], p0, p1);
+        cull_unpack(p0, p1, out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+    }
+}
 // block test used by the blend kernels
 int hc_cull_miss(float u, float v, const float* conic, float opacity, float x0, float y0, float w, float h) {
     float hx, hy, hs, ht, p0, p1;
