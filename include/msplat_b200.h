@@ -101,6 +101,17 @@ size_t msb_sort_workspace_bytes(int P, long long M, int W, int H);
 int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int P,
                       long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws,
                       size_t ws_bytes, int sm_count, void* stream);
+/* View batch: ONE sort for `views` views of the same P Gaussians (the batch is a virtual scene of
+ * views * P Gaussians on views * T tiles).  uv/depth/radius/tiles are [views, P] view-major (P a multiple
+ * of 4 when views > 1); idx_sorted [M] receives view * P + index, tile_range [views * T, 2] indexes
+ * idx_sorted; M = sum of tiles over the batch.  Limits: M <= 2^31 - 1 (int32 positions, like the
+ * reference's int32 cumsum, msplat/sort_gaussian.py:42), views * P and views * T < 2^31.  Within a view
+ * the order is exactly that of msb_sort_gaussian. */
+int msb_sort_num_passes_views(int W, int H, int views);
+size_t msb_sort_workspace_bytes_views(int P, int views, long long M, int W, int H);
+int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles,
+                            int P, int views, long long M, int W, int H, int32_t* idx_sorted,
+                            int32_t* tile_range, void* ws, size_t ws_bytes, int sm_count, void* stream);
 
 /* ---- alpha_blending -----------------------------------------------------------------------
  * replaces alphaBlendingForward / alphaBlendingBackward (src/alpha_blending.cu:248-573)
@@ -133,6 +144,16 @@ int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* id
 int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
                          const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream);
+/* View batch in one grid (blockIdx.z = view): rec [views*P,8], featp [views*P,Cpad], idx_sorted and
+ * tile_range [views*T,2] from msb_sort_gaussian_views; image / dL_dimage [views,C,H,W], final_T /
+ * ncontrib [views,H,W]; grec [views*P,8], gfeat [views*P,Cpad] (P = rows per view). */
+int msb_blend_packed_fwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
+                               const int32_t* tile_range, float bg, int C, int W, int H, int views, float* image,
+                               float* final_T, int32_t* ncontrib, void* stream);
+int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
+                               const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
+                               const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
+                               float* gfeat, int already_zero, void* stream);
 
 /* ---- fused SH render preprocess ------------------------------------------------------------
  * One forward / one backward kernel for the whole per-Gaussian part of an SH-coloured render:
@@ -159,6 +180,50 @@ int msb_render_preprocess_bwd(const float* xyz, const float* scale, const float*
                               const float* gfeat, int P, int Cs, int D, int with_depth, float sh_bias, int clamp,
                               int accumulate, float* dL_dxyz, float* dL_dscale, float* dL_dquat, float* dL_dopacity,
                               float* dL_dshs, float* dL_dintr, float* dL_dextr, void* stream);
+
+/* Diagnostic used by bench.py for the blend roofline: blended [views,H,W] int32 = number of list entries
+ * that actually blend at each pixel (pass the power / alpha tests of src/alpha_blending.cu:85-94 before
+ * the pixel terminates).  Same traversal as the forward kernel, no colours. */
+int msb_blend_packed_count(const float* rec, const int32_t* idx_sorted, const int32_t* tile_range, int W, int H,
+                           int views, int32_t* blended, void* stream);
+
+/* View batch: ONE launch for `views` cameras over the same Gaussians (parameters and SH rows are read
+ * once; the backward sums the gradients over the views in registers / at the L2).  intr [views,4];
+ * extr [views,estride], estride = 12 ([3,4]) or 16 ([4,4]).  Per-view buffers are view-major with
+ * `vstride` rows per view (vstride >= P, a multiple of 4 when views > 1; rows >= P are not touched):
+ * rec [views,vstride,8], featp [views,vstride,Cpad], uv [views,vstride,2], depth / radius / tiles
+ * [views,vstride], grec / gfeat like rec / featp; total_dev [views] int64 (optional) = M per view.
+ * backward: per-Gaussian pointers may be offset to a slab of P Gaussians (tiles / grec / gfeat to the same
+ * row of view 0).  row_index [P] (optional): dL_dshs row of Gaussian i is row_index[i] - row_base of a compact
+ * [rows,Cs,D] buffer, negative = no row.  dL_dintr [views,4] / dL_dextr [views,estride] optional,
+ * accumulated into; dL_dextr includes the view direction's dependence on the camera centre -R^T t. */
+int msb_render_preprocess_fwd_views(const float* xyz, const float* scale, const float* quat, const float* opacity,
+                                    const float* shs, const float* intr, const float* extr, int estride, int P,
+                                    int views, long long vstride, int Cs, int D, int with_depth, int W, int H,
+                                    float nearest, float extent, float sh_bias, int clamp, float* rec, float* featp,
+                                    float* uv, float* depth, int32_t* radius, int32_t* tiles, long long* total_dev,
+                                    void* stream);
+int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const float* quat, const float* shs,
+                                    const float* intr, const float* extr, int estride, const int32_t* tiles,
+                                    const float* grec, const float* gfeat, const int32_t* row_index, int row_base,
+                                    int P, int views, long long vstride, int Cs, int D, int with_depth,
+                                    float sh_bias, int clamp, int accumulate, float* dL_dxyz, float* dL_dscale,
+                                    float* dL_dquat, float* dL_dopacity, float* dL_dshs, float* dL_dintr,
+                                    float* dL_dextr, void* stream);
+
+/* ---- view-batch data parallelism: exchange only the dL_dshs rows some rank touched ------------------
+ * (no reference counterpart: the reference has no distributed code)
+ * msb_grad_live_mask: mask [P] int32 = 1 where any view's gfeat [views,vstride,Cpad] row is non-zero.
+ * msb_grad_row_index: after the masks were summed over the ranks: incl [P] = inclusive count of
+ *   mask > 0, row_index [P] = incl - 1 where mask > 0 else -1; the count goes to *total_host (PINNED,
+ *   asynchronous); ws = msb_sort_scan_workspace_bytes(P).
+ * msb_grad_expand_rows: dense [P,row_floats] <- compact[row_index[i] - row_base], zeros where < 0. */
+int msb_grad_live_mask(const float* gfeat, int P, int views, long long vstride, int Cpad, int32_t* mask,
+                       void* stream);
+int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_index, long long* total_host,
+                       void* ws, size_t ws_bytes, void* stream);
+int msb_grad_expand_rows(const float* compact, const int32_t* row_index, int row_base, int P, int row_floats,
+                         float* dense, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ from .compute_sh import compute_sh
 from .ewa_project import ewa_project
 from .project_point import project_point
 from .render import rasterization_sh, rasterization_sh_views
-from .sort_gaussian import sort_gaussian
+from .sort_gaussian import sort_gaussian, sort_gaussian_views
 
 __all__ = [
     "project_point",
@@ -30,6 +30,7 @@ __all__ = [
     # extensions beyond the reference API (fused SH render path, csrc/render.cu)
     "rasterization_sh",
     "rasterization_sh_views",
+    "sort_gaussian_views",
 ]
 
 __version__ = "0.1.0"

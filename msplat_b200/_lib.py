@@ -19,8 +19,9 @@ LIB_PATH = os.path.join(_HERE, "libmsplat_b200.so")
 _lib = None
 _lock = threading.Lock()
 
-# Per-process launch counter: bench.py reports it as "gpu_launches".
+# Per-process launch counter: bench.py reports it as "gpu_launches" (updated under _count_lock).
 _launches = 0
+_count_lock = threading.Lock()
 
 # kernels launched by each C-ABI entry point (see csrc/*.cu); a tuple means (fixed, per-pass)
 _KERNELS_PER_CALL = {}
@@ -56,6 +57,19 @@ def _declare(lib):
         "msb_blend_packed_bwd": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, P, I, V]),
         "msb_render_preprocess_fwd": (I, [P] * 7 + [I, I, I, I, I, I, F, F, F, I] + [P] * 8 + [V]),
         "msb_render_preprocess_bwd": (I, [P] * 9 + [I, I, I, I, F, I, I] + [P] * 7 + [V]),
+        # view batches
+        "msb_sort_num_passes_views": (I, [I, I, I]),
+        "msb_sort_workspace_bytes_views": (SZ, [I, I, LL, I, I]),
+        "msb_sort_gaussian_views": (I, [P, P, P, P, I, I, LL, I, I, P, P, P, SZ, I, V]),
+        "msb_blend_packed_fwd_views": (I, [P, P, P, P, F, I, I, I, I, P, P, P, V]),
+        "msb_blend_packed_bwd_views": (I, [P, P, P, P, F, I, I, I, I, I, P, P, P, P, P, I, V]),
+        "msb_blend_packed_count": (I, [P, P, P, I, I, I, P, V]),
+        "msb_render_preprocess_fwd_views": (I, [P] * 7 + [I, I, I, LL, I, I, I, I, I, F, F, F, I] + [P] * 7 + [V]),
+        "msb_render_preprocess_bwd_views": (I, [P] * 6 + [I] + [P] * 4 + [I, I, I, LL, I, I, I, F, I, I] + [P] * 7 + [V]),
+        # view-batch data parallelism
+        "msb_grad_live_mask": (I, [P, I, I, LL, I, P, V]),
+        "msb_grad_row_index": (I, [P, I, P, P, P, P, SZ, V]),
+        "msb_grad_expand_rows": (I, [P, P, I, I, I, P, V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
@@ -111,12 +125,14 @@ def call(what: str, nlaunch: int, fn, device, *args):
         else:
             rc = fn(*args, st)
     check(rc, what)
-    _launches += nlaunch
+    with _count_lock:
+        _launches += nlaunch
 
 
 def count_launches(n: int):
     global _launches
-    _launches += n
+    with _count_lock:
+        _launches += n
 
 
 def launches() -> int:

@@ -101,23 +101,29 @@ __device__ __forceinline__ void stage_issue(Stage<CH, B>& st, int slot, int id, 
 // The per-pair body has no divergent branches: a pair that fails a test blends with weight 0
 // (ffma(T, 0 * f, F) == F), so the image is bit-identical to a branching formulation and to the
 // reference, and a warp-visit costs ~40 issue slots.
-template <int CH>
+// COUNT (diagnostic, bench.py): instead of colours the kernel writes, per pixel, the number of list entries
+// that actually blend (pass the power / alpha tests before termination) into `image` reinterpreted as int32
+// [views,H,W] -- the "blended pairs" the roofline of the blend kernels is computed on.
+template <int CH, bool COUNT = false>
 __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
                                                           int c_valid, int W, int H, int write_aux,
                                                           float* __restrict__ final_T, int* __restrict__ ncontrib,
-                                                          float* __restrict__ image) {
+                                                          float* __restrict__ image, long long img_vstride) {
     extern __shared__ __align__(16) unsigned char bl_raw[];
     Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
-    const int tile = blockIdx.y * gxt + blockIdx.x;
+    // blockIdx.z = view of a view batch: tile ids, Gaussian ids and tile ranges are those of the batch's
+    // single sort (view * T + tile, view * P + index); images / final_T / ncontrib are [views, ...]
+    const int view = blockIdx.z;
+    const int tile = (view * (int)gridDim.y + blockIdx.y) * gxt + blockIdx.x;
     const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const float wx0 = (float)bx0, wy0 = (float)by0;
     const bool inside = px < W && py < H;
     bool done = !inside;
 
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
 
     float T = 1.0f;
     int last = 0;
+    int nblend = 0;
     float F[CH];  // accumulated colour
 #pragma unroll
     for (int k = 0; k < CH; ++k) F[k] = 0.f;
@@ -189,21 +196,27 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
                 }
                 T = blend ? nT : T;
                 last = blend ? base1 + j : last;
+                if (COUNT) nblend += blend ? 1 : 0;
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
     }
     cp_async_wait<0>();
     if (inside) {
+        const long long hw = (long long)H * W;
         const long long pix = (long long)py * W + px;
         if (write_aux) {
-            final_T[pix] = T;
-            ncontrib[pix] = last;
+            final_T[view * hw + pix] = T;
+            ncontrib[view * hw + pix] = last;
         }
-        const long long hw = (long long)H * W;
+        if (COUNT) {
+            reinterpret_cast<int*>(image)[view * hw + pix] = nblend;
+        } else {
+            float* img = image + view * img_vstride;
 #pragma unroll
-        for (int k = 0; k < CH; ++k)
-            if (k < c_valid) image[k * hw + pix] = ffma(T, bg, F[k]);
+            for (int k = 0; k < CH; ++k)
+                if (k < c_valid) img[k * hw + pix] = ffma(T, bg, F[k]);
+        }
     }
 }
 
@@ -330,6 +343,7 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
                                                           const float* __restrict__ final_T,
                                                           const int* __restrict__ ncontrib,
                                                           const float* __restrict__ dL_dimage,
+                                                          long long img_vstride,
                                                           float* __restrict__ grec, float* __restrict__ gfeat,
                                                           int geom_grads) {
     extern __shared__ __align__(16) unsigned char bl_raw[];
@@ -342,14 +356,18 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
     __shared__ int s_max[BL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
-    const int tile = blockIdx.y * gxt + blockIdx.x;
+    const int view = blockIdx.z;  // see blend_fwd_kernel
+    const int tile = (view * (int)gridDim.y + blockIdx.y) * gxt + blockIdx.x;
     const int bx0 = blockIdx.x * MSB_TILE + (warp & 1) * 8, by0 = blockIdx.y * MSB_TILE + (warp >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const float wx0 = (float)bx0, wy0 = (float)by0;
     const bool inside = px < W && py < H;
-    const long long pix = (long long)py * W + px;
     const long long hw = (long long)H * W;
+    const long long pix = (long long)py * W + px;
+    final_T += view * hw;
+    ncontrib += view * hw;
+    dL_dimage += view * img_vstride;
 
     const int2 range = tile_range[tile];
     const int lc = inside ? min(ncontrib[pix], range.y - range.x) : 0;  // this pixel's last contributor
@@ -505,7 +523,7 @@ static inline int pick_bwd_ch(int rem) { return rem >= 16 ? 16 : rem > 4 ? 8 : 4
 template <int CH>
 static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, int write_aux,
-                      float* final_T, int* ncontrib, float* image) {
+                      float* final_T, int* ncontrib, float* image, long long img_vstride) {
     const size_t smem = 2 * sizeof(Stage<CH>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(blend_fwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -513,7 +531,7 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_fwd: cudaFuncSetAttribute failed");
     }
     blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
-                                                    final_T, ncontrib, image);
+                                                    final_T, ncontrib, image, img_vstride);
     return check_launch("alpha_blending_fwd");
 }
 
@@ -532,7 +550,8 @@ static int blend_bwd_cfg() {
 template <int CH, int B, int MINB>
 static int launch_bwd_cfg(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                           const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
-                          const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
+                          const int* ncontrib, const float* dL_dimage, long long img_vstride, float* grec, float* gfeat,
+                          int geom) {
     const size_t smem = Bwd3<CH, B>::SMEM;
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -540,15 +559,17 @@ static int launch_bwd_cfg(dim3 grid, cudaStream_t st, const float4* rec, const f
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
     }
     blend_bwd_kernel<CH, B, MINB><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                             final_T, ncontrib, dL_dimage, grec, gfeat, geom);
+                                                             final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat,
+                                                             geom);
     return check_launch("alpha_blending_bwd");
 }
 
 template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
-                      const int* ncontrib, const float* dL_dimage, float* grec, float* gfeat, int geom) {
-#define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, grec, gfeat, geom
+                      const int* ncontrib, const float* dL_dimage, long long img_vstride, float* grec, float* gfeat,
+                      int geom) {
+#define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat, geom
     if constexpr (CH == 4) {
         switch (blend_bwd_cfg()) {
             case 1: return launch_bwd_cfg<CH, 128, 3>(MSB_BWD_ARGS);
@@ -565,10 +586,12 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float
 }
 
 // channel-chunk dispatcher of the forward pass (reference D1: alpha_blending.cu:248-394)
+// views > 1: one grid for a whole view batch (blockIdx.z = view), image [views, C, H, W]
 static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H, float* image,
-                          float* final_T, int32_t* ncontrib) {
-    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+                          float* final_T, int32_t* ncontrib, int views = 1) {
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE, views);
+    const long long vs = (long long)C * H * W;
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
     int c0 = 0, first = 1;
     do {  // at least one pass so that final_T / ncontrib exist even for C == 0
@@ -579,19 +602,19 @@ static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
         int rc;
         if (C == 0) {  // geometry-only pass: stage rec twice (no feature rows exist)
             rc = launch_fwd<4>(grid, st, rec, reinterpret_cast<const float*>(rec), 8, 0, idx_sorted, tr, bg, 0, W, H, 1,
-                               final_T, ncontrib, img);
+                               final_T, ncontrib, img, vs);
         } else if (ch == 32) {
             rc = launch_fwd<32>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img);
+                                ncontrib, img, vs);
         } else if (ch == 16) {
             rc = launch_fwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img);
+                                ncontrib, img, vs);
         } else if (ch == 8) {
             rc = launch_fwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img);
+                               ncontrib, img, vs);
         } else {
             rc = launch_fwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img);
+                               ncontrib, img, vs);
         }
         if (rc) return rc;
         c0 += ch;
@@ -604,8 +627,9 @@ static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
 static int run_bwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H,
                           const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
-                          float* gfeat) {
-    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE);
+                          float* gfeat, int views = 1) {
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE, views);
+    const long long vs = (long long)C * H * W;
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
     for (int c0 = 0; c0 < C;) {
         const int rem = Cpad - c0;
@@ -617,13 +641,13 @@ static int run_bwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
         // reference does the same, alpha_blending.cu:436-567)
         if (ch == 16)
             rc = launch_bwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                                dimg, grec, gfeat, 1);
+                                dimg, vs, grec, gfeat, 1);
         else if (ch == 8)
             rc = launch_bwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, grec, gfeat, 1);
+                               dimg, vs, grec, gfeat, 1);
         else
             rc = launch_bwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, grec, gfeat, 1);
+                               dimg, vs, grec, gfeat, 1);
         if (rc) return rc;
         c0 += ch;
     }
@@ -683,16 +707,38 @@ int msb_alpha_blending_fwd(const float* uv, const float* conic, const float* opa
 
 // Forward on inputs that are already in the packed layout (rec [P,8], featp [P,Cpad] with
 // Cpad = msb_blend_cpad(C)): what msb_render_preprocess_fwd produces.
-int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
-                         float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
-                         void* stream) {
+// views > 1: a view batch in one grid.  rec [views*P,8], featp [views*P,Cpad], idx_sorted and
+// tile_range [views*T,2] from msb_sort_gaussian_views; image [views,C,H,W], final_T / ncontrib [views,H,W].
+int msb_blend_packed_fwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
+                               const int32_t* tile_range, float bg, int C, int W, int H, int views, float* image,
+                               float* final_T, int32_t* ncontrib, void* stream) {
     // rec / featp may be NULL for an empty cloud (every tile range is then (0, 0))
-    if (C < 0 || W <= 0 || H <= 0 || !tile_range || !final_T || !ncontrib || (C > 0 && !image))
+    if (C < 0 || W <= 0 || H <= 0 || views <= 0 || views > 65535 || !tile_range || !final_T || !ncontrib ||
+        (C > 0 && !image))
         return set_error(MSB_ERR_ARG, "blend_packed_fwd: bad argument");
     if ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(featp)) & 15u)
         return set_error(MSB_ERR_ARG, "blend_packed_fwd: 16-byte alignment");
     return run_fwd_passes((cudaStream_t)stream, reinterpret_cast<const float4*>(rec), featp, msb_blend_cpad(C), C,
-                          idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib);
+                          idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib, views);
+}
+// Diagnostic (bench.py): blended [views,H,W] int32 = list entries that blend at each pixel.
+int msb_blend_packed_count(const float* rec, const int32_t* idx_sorted, const int32_t* tile_range, int W, int H,
+                           int views, int32_t* blended, void* stream) {
+    if (W <= 0 || H <= 0 || views <= 0 || views > 65535 || !tile_range || !blended)
+        return set_error(MSB_ERR_ARG, "blend_packed_count: bad argument");
+    const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE, views);
+    // features are not needed: the records are staged twice (as in the C == 0 pass of run_fwd_passes)
+    blend_fwd_kernel<4, true><<<grid, BL_NT, 2 * sizeof(Stage<4>), (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(rec), rec, 8, 0, idx_sorted, reinterpret_cast<const int2*>(tile_range), 0.f, 0,
+        W, H, 0, nullptr, nullptr, reinterpret_cast<float*>(blended), 0);
+    return check_launch("blend_packed_count");
+}
+
+int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
+                         float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
+                         void* stream) {
+    return msb_blend_packed_fwd_views(rec, featp, idx_sorted, tile_range, bg, C, W, H, 1, image, final_T, ncontrib,
+                                      stream);
 }
 
 // Backward.  `packed` is the buffer produced by the forward call on the same inputs.
@@ -726,22 +772,37 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
 // Backward on packed inputs; the gradients stay packed: grec [P,8] = {dL_duv.xy, dL_dconic.xyz,
 // dL_dopacity, 0, 0}, gfeat [P,Cpad].  Both are zeroed by this call and consumed by
 // msb_render_preprocess_bwd.
+int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
+                               const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
+                               const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
+                               float* gfeat, int already_zero, void* stream);
 int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
                          const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream) {
+    return msb_blend_packed_bwd_views(rec, featp, idx_sorted, tile_range, bg, P, C, W, H, 1, final_T, ncontrib,
+                                      dL_dimage, grec, gfeat, already_zero, stream);
+}
+
+// View batch (see msb_blend_packed_fwd_views): P = Gaussians per view; grec [views*P,8], gfeat [views*P,Cpad],
+// dL_dimage [views,C,H,W].
+int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
+                               const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
+                               const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
+                               float* gfeat, int already_zero, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (P < 0 || C < 0 || W <= 0 || H <= 0) return set_error(MSB_ERR_ARG, "blend_packed_bwd: bad argument");
+    if (P < 0 || C < 0 || W <= 0 || H <= 0 || views <= 0 || views > 65535)
+        return set_error(MSB_ERR_ARG, "blend_packed_bwd: bad argument");
     if (P == 0) return MSB_OK;
     if (!rec || !featp || !tile_range || !final_T || !ncontrib || !grec || !gfeat || (C > 0 && !dL_dimage))
         return set_error(MSB_ERR_ARG, "blend_packed_bwd: null pointer");
     const int Cpad = msb_blend_cpad(C);
     if (!already_zero) {  // the kernels accumulate with reductions: the packed gradients start from zero
-        cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)P * 8 * sizeof(float), st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(gfeat, 0, (size_t)P * Cpad * sizeof(float), st);
+        cudaError_t e = cudaMemsetAsync(grec, 0, (size_t)views * P * 8 * sizeof(float), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(gfeat, 0, (size_t)views * P * Cpad * sizeof(float), st);
         if (e != cudaSuccess) return set_error((int)e, "blend_packed_bwd: memset failed");
     }
     return run_bwd_passes(st, reinterpret_cast<const float4*>(rec), featp, Cpad, C, idx_sorted, tile_range, bg, W, H,
-                          final_T, ncontrib, dL_dimage, grec, gfeat);
+                          final_T, ncontrib, dL_dimage, grec, gfeat, views);
 }
 
 }  // extern "C"

@@ -288,8 +288,11 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 
 }  // namespace msb
 
+// ---- the public C ABI: every translation unit sees the prototypes it defines, so a definition that
+// drifts from include/msplat_b200.h is a compile error (conflicting C-linkage declarations) ---------
+#include "../../include/msplat_b200.h"
+
 // ---- host-side error plumbing (defined in capi.cu) ------------------------------------------
-extern "C" const char* msb_last_error(void);
 namespace msb {
 int set_error(int code, const char* msg);
 int check_launch(const char* what);

@@ -82,9 +82,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp /*[NTH/32 + 1]
     return res;
 }
 
-// value i of the scanned sequence
-__device__ __forceinline__ int scan_value(const int* __restrict__ vals, long long i) { return max(vals[i], 0); }
+// value i of the scanned sequence (BIN: 1 where vals[i] > 0 -- counts instead of sums)
+template <bool BIN = false>
+__device__ __forceinline__ int scan_value(const int* __restrict__ vals, long long i) {
+    return BIN ? (vals[i] > 0 ? 1 : 0) : max(vals[i], 0);
+}
 
+template <bool BIN = false>
 __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int* __restrict__ vals,
                                                                 long long* __restrict__ bsum) {
     __shared__ long long s_part[SC_NT / 32];
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k * SC_NT + threadIdx.x;
-        if (i < P) acc += scan_value(vals, i);
+        if (i < P) acc += scan_value<BIN>(vals, i);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(int nb, long long* __r
 }
 
 // out[i] = (EXCL ? exclusive : inclusive) prefix of the sequence
-template <bool EXCL>
+template <bool EXCL, bool BIN = false>
 __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __restrict__ vals,
                                                            const long long* __restrict__ bsum,
                                                            int* __restrict__ out) {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k;
-        v[k] = i < P ? scan_value(vals, i) : 0;
+        v[k] = i < P ? scan_value<BIN>(vals, i) : 0;
         sum += v[k];
     }
     int total;
@@ -170,6 +174,13 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
             if (i < P) out[i] = run;  // inclusive, like torch.cumsum
         }
     }
+}
+
+// row_index[i] = mask[i] > 0 ? incl[i] - 1 : -1 (incl = inclusive prefix count of mask > 0)
+__global__ void __launch_bounds__(256) row_index_kernel(int P, const int* __restrict__ mask,
+                                                        const int* __restrict__ incl, int* __restrict__ row_index) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) row_index[i] = mask[i] > 0 ? incl[i] - 1 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,9 +199,14 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 constexpr int KG_NT = 256;
 constexpr int KG_WARPS = KG_NT / 32;
 constexpr int MAX_TPASS = 4;  // tile id < 2^31
-constexpr unsigned int RS_FLAG_AGG = 1u << 30;
-constexpr unsigned int RS_FLAG_PRE = 2u << 30;
-constexpr unsigned int RS_VALUE_MASK = (1u << 30) - 1u;
+// Status word of the chained scans / decoupled look-backs: 0 = nothing published yet; bit 31 set =
+// inclusive PREFIX (31-bit value); otherwise an AGGREGATE stored as value + 1.  Every value is
+// < 2^31, the bound the reference's int32 cumsum puts on M (msplat/sort_gaussian.py:42).
+constexpr unsigned int RS_PRE_BIT = 0x80000000u;
+__device__ __forceinline__ unsigned int rs_agg(unsigned int v) { return v + 1u; }
+__device__ __forceinline__ unsigned int rs_pre(unsigned int v) { return v | RS_PRE_BIT; }
+__device__ __forceinline__ bool rs_is_pre(unsigned int w) { return (w & RS_PRE_BIT) != 0u; }
+__device__ __forceinline__ unsigned int rs_value(unsigned int w) { return rs_is_pre(w) ? (w & ~RS_PRE_BIT) : (w - 1u); }
 
 __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
     unsigned int v;
@@ -218,7 +234,12 @@ __device__ __forceinline__ int keygen_count(int slots, int rad, float2 p, int gx
 
 constexpr int KG_ROWS = 4;  // rows of 32 Gaussians whose loads are issued together (memory-level parallelism)
 
-__global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int seg /*Gaussians per warp, multiple of 32*/,
+// View batches (views > 1): the arrays hold views * Pv entries, view-major; entry i belongs to view
+// i / Pv and its tile rectangle is shifted down by view * gy rows of a virtual gx x (views gy) grid, so
+// that the whole batch is ONE sort whose tile id is view * T + tile and whose Gaussian id is
+// view * Pv + index (what the batched blend kernels index their packed records with).
+__global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int Pv /*Gaussians per view*/,
+                                                       int seg /*Gaussians per warp, multiple of 32*/,
                                                        const float2* __restrict__ uv,
                                                        const float* __restrict__ depth,
                                                        const int* __restrict__ radius,
@@ -272,7 +293,7 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int seg /*Gaussian
         wpre += w < warp ? c : 0u;
         total += c;
     }
-    if (threadIdx.x == 0) st_relaxed(status + vcta, RS_FLAG_PRE | total);
+    if (threadIdx.x == 0) st_relaxed(status + vcta, rs_pre(total));
 
     // ---- prefix over the virtual CTAs before this one (all of them have started) -----------------
     unsigned int part = 0;
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int seg /*Gaussian
             __nanosleep(20);
             v = ld_relaxed(status + j);
         }
-        part += v & RS_VALUE_MASK;
+        part += rs_value(v);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int seg /*Gaussian
                 const unsigned int o = pos + __popc(em & lt_mask);
                 dkeys[o] = dk[r];
                 dvals[o] = (int)i;
-                rect[i] = make_int4(x0, y0, w, n);
+                rect[i] = make_int4(x0, y0 + (int)(i / Pv) * gy, w, n);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((dk[r] >> (8 * p)) & 255u)], 1u);
             }
@@ -374,7 +395,7 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
         // few tiles (all resident at once on this GPU up to ~1.8 M emitters): every tile publishes its total
         // and sums the totals of ALL tiles before it -- one round trip instead of a look-back chain
         __shared__ unsigned int s_part[SC_NT / 32];
-        if (threadIdx.x == 0) st_relaxed(status + tile, RS_FLAG_PRE | (unsigned)total);
+        if (threadIdx.x == 0) st_relaxed(status + tile, rs_pre((unsigned)total));
         unsigned int part = 0;
         for (int j = threadIdx.x; j < tile; j += SC_NT) {
             unsigned int w = ld_relaxed(status + j);
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
                 __nanosleep(20);
                 w = ld_relaxed(status + j);
             }
-            part += w & RS_VALUE_MASK;
+            part += rs_value(w);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -397,16 +418,16 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
     } else if (warp == 0) {
         unsigned int pre = 0;
         if (tile > 0) {
-            if (lane == 0) st_relaxed(status + tile, RS_FLAG_AGG | (unsigned)total);
+            if (lane == 0) st_relaxed(status + tile, rs_agg((unsigned)total));
             int j = tile - 1;
             while (true) {
-                const unsigned int w = (j - lane >= 0) ? ld_relaxed(status + (j - lane)) : RS_FLAG_PRE;
-                const unsigned ready = __ballot_sync(0xffffffffu, (w & ~RS_VALUE_MASK) != 0u);
-                const unsigned isp = __ballot_sync(0xffffffffu, (w & RS_FLAG_PRE) != 0u);
+                const unsigned int w = (j - lane >= 0) ? ld_relaxed(status + (j - lane)) : RS_PRE_BIT;
+                const unsigned ready = __ballot_sync(0xffffffffu, w != 0u);
+                const unsigned isp = __ballot_sync(0xffffffffu, rs_is_pre(w));
                 const int run = (~ready) ? __ffs(~ready) - 1 : 32;  // predecessors ready without a gap
                 const int fp = isp ? __ffs(isp) - 1 : 32;           // nearest one holding a full prefix
                 const int take = min(run, fp + 1);
-                unsigned int add = lane < take ? (w & RS_VALUE_MASK) : 0u;
+                unsigned int add = lane < take ? rs_value(w) : 0u;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
                 pre += add;
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
             }
         }
         if (lane == 0) {
-            st_relaxed(status + tile, RS_FLAG_PRE | (pre + (unsigned)total));
+            st_relaxed(status + tile, rs_pre(pre + (unsigned)total));
             s_prefix = pre;
         }
     }
@@ -684,7 +705,7 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
     }
     if (tid == 255) count -= (unsigned)(TILE - valid);  // padding keys are not real
     unsigned int* my_status = status + (size_t)tile * 256 + tid;
-    if (tile != 0) st_relaxed(my_status, RS_FLAG_AGG | count);  // as early as possible: successors sum it
+    if (tile != 0) st_relaxed(my_status, rs_agg(count));  // as early as possible: successors sum it
 
     // tile-local exclusive digit offsets; tile 0 also scans the global histogram and folds the
     // global digit base into the prefix it publishes, so every other tile receives it through
@@ -694,7 +715,7 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
     unsigned int excl = 0;
     if (tile == 0) {
         excl = (unsigned)block_excl_scan<RS_NT>((int)hist[tid], sm.scan_tmp, tot);
-        st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
+        st_relaxed(my_status, rs_pre(excl + count));
     } else {
         // decoupled look-back, LB predecessors per round trip (independent loads in flight);
         // a serial walk costs one L2 latency per predecessor and dominated the pass
@@ -703,15 +724,15 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
             unsigned int v[LB];
 #pragma unroll
             for (int k = 0; k < LB; ++k)
-                v[k] = (j - k >= 0) ? ld_relaxed(status + (size_t)(j - k) * 256 + tid) : RS_FLAG_PRE;
+                v[k] = (j - k >= 0) ? ld_relaxed(status + (size_t)(j - k) * 256 + tid) : RS_PRE_BIT;
             int used = 0;
             bool done = false;
 #pragma unroll
             for (int k = 0; k < LB; ++k) {
-                if (!done && used == k && (v[k] & ~RS_VALUE_MASK) != 0u) {
-                    excl += v[k] & RS_VALUE_MASK;
+                if (!done && used == k && v[k] != 0u) {
+                    excl += rs_value(v[k]);
                     used = k + 1;
-                    done = (v[k] & RS_FLAG_PRE) != 0u;
+                    done = rs_is_pre(v[k]);
                 }
             }
             if (done) break;
@@ -721,14 +742,14 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
                 // written together), so waiting warps do not take issue slots from the tiles still ranking
                 if (__all_sync(0xffffffffu, used == 0)) {
                     if (lane == 0)
-                        while ((ld_relaxed(status + (size_t)j * 256 + tid) & ~RS_VALUE_MASK) == 0u) __nanosleep(gate_ns);
+                        while (ld_relaxed(status + (size_t)j * 256 + tid) == 0u) __nanosleep(gate_ns);
                     __syncwarp();
                 }
             } else if (used == 0) {
                 __nanosleep(20);
             }
         }
-        st_relaxed(my_status, RS_FLAG_PRE | (excl + count));
+        st_relaxed(my_status, rs_pre(excl + count));
     }
     sm.gadj[tid] = (int)excl - (int)lbase;
 #pragma unroll
@@ -868,7 +889,7 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
     const int nb = (P + SC_TILE - 1) / SC_TILE;
     long long* bsum = reinterpret_cast<long long*>(ws);
     long long* total_dev = bsum + nb;
-    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
+    scan_block_sums_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
     scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
     if (offsets) scan_apply_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, bsum, offsets);
     int rc = check_launch("sort_scan");
@@ -878,28 +899,66 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
     return MSB_OK;
 }
 
+// Compact row indices for the data-parallel gradient exchange (msplat_b200/render.py): incl [P] =
+// inclusive count of mask > 0, row_index [P] = incl - 1 where mask > 0 else -1; the count of set entries is
+// copied asynchronously to *total_host (pinned).  ws: msb_sort_scan_workspace_bytes(P).
+int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_index, long long* total_host, void* ws,
+                       size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || !total_host) return set_error(MSB_ERR_ARG, "grad_row_index: bad argument");
+    if (P == 0) {
+        *total_host = 0;
+        return MSB_OK;
+    }
+    if (!mask || !incl || !row_index || !ws) return set_error(MSB_ERR_ARG, "grad_row_index: null pointer");
+    if (ws_bytes < msb_sort_scan_workspace_bytes(P)) return set_error(MSB_ERR_WORKSPACE, "grad_row_index: workspace too small");
+    const int nb = (P + SC_TILE - 1) / SC_TILE;
+    long long* bsum = reinterpret_cast<long long*>(ws);
+    long long* total_dev = bsum + nb;
+    scan_block_sums_kernel<true><<<nb, SC_NT, 0, st>>>(P, mask, bsum);
+    scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
+    scan_apply_kernel<false, true><<<nb, SC_NT, 0, st>>>(P, mask, bsum, incl);
+    row_index_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, mask, incl, row_index);
+    int rc = check_launch("grad_row_index");
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return set_error((int)e, "grad_row_index: cudaMemcpyAsync failed");
+    return MSB_OK;
+}
+
 // Number of 8-bit digit passes over the 64-bit key: 4 depth passes (on the Gaussians) plus the
-// tile-id passes (on the duplicates).
-int msb_sort_num_passes(int W, int H) {
-    const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
-    return 4 + tile_passes(gx * gy);
+// tile-id passes (on the duplicates).  A batch of `views` views sorts (view * T + tile) ids.
+int msb_sort_num_passes_views(int W, int H, int views) {
+    const long long gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
+    const long long T = gx * gy * (views > 0 ? views : 1);
+    return 4 + tile_passes((int)min(T, (long long)INT32_MAX));
 }
+int msb_sort_num_passes(int W, int H) { return msb_sort_num_passes_views(W, H, 1); }
 
-size_t msb_sort_workspace_bytes(int P, long long M, int W, int H) {
-    const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
-    if (M <= 0 || P <= 0) return 256;
-    return sort_layout(P, M, gx * gy).total;
+size_t msb_sort_workspace_bytes_views(int P, int views, long long M, int W, int H) {
+    const long long gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
+    const long long Pt = (long long)P * views, T = gx * gy * views;
+    if (M <= 0 || P <= 0 || views <= 0 || Pt > INT32_MAX || T > INT32_MAX) return 256;
+    return sort_layout((int)Pt, M, (int)T).total;
 }
+size_t msb_sort_workspace_bytes(int P, long long M, int W, int H) { return msb_sort_workspace_bytes_views(P, 1, M, W, H); }
 
-// Phase 2.  idx_sorted[M] (int32) and tile_range[T, 2] (int32) are outputs owned by the caller.
-int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int P,
-                      long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws, size_t ws_bytes,
-                      int sm_count, void* stream) {
+// Phase 2 for a batch of `views` views over the same P Gaussians (views = 1: the reference's call).
+// uv/depth/radius/tiles hold [views, P] entries, view-major.  idx_sorted [M] receives view * P + index,
+// tile_range [views * T, 2] indexes idx_sorted; M = sum of tiles over the whole batch, < 2^31.
+int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int Pv,
+                            int views, long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws,
+                            size_t ws_bytes, int sm_count, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
-    const int T = gx * gy;
-    if (P < 0 || M < 0 || W <= 0 || H <= 0 || !tile_range) return set_error(MSB_ERR_ARG, "sort_gaussian: bad argument");
-    if (M >= (1ll << 30)) return set_error(MSB_ERR_RANGE, "sort_gaussian: more than 2^30 tile intersections");
+    if (Pv < 0 || views <= 0 || M < 0 || W <= 0 || H <= 0 || !tile_range)
+        return set_error(MSB_ERR_ARG, "sort_gaussian: bad argument");
+    if ((long long)Pv * views > INT32_MAX || (long long)gx * gy * views > INT32_MAX)
+        return set_error(MSB_ERR_RANGE, "sort_gaussian: views * P and views * tiles must stay below 2^31");
+    // int32 positions, like the reference's int32 cumsum (msplat/sort_gaussian.py:42)
+    if (M > (long long)INT32_MAX) return set_error(MSB_ERR_RANGE, "sort_gaussian: more than 2^31 - 1 tile intersections");
+    const int P = Pv * views;
+    const int T = gx * gy * views;
     cudaError_t e = cudaMemsetAsync(tile_range, 0, (size_t)T * 2 * sizeof(int32_t), st);
     if (e != cudaSuccess) return set_error((int)e, "sort_gaussian: memset tile_range failed");
     if (M == 0 || P == 0) return MSB_OK;
@@ -925,7 +984,7 @@ int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     const long long per_warp = ((long long)P + (long long)kgrid * KG_WARPS - 1) / ((long long)kgrid * KG_WARPS);
     const int seg = (int)((per_warp + 31) / 32 * 32);
     if ((size_t)kgrid > (size_t)L.nchunks_k) return set_error(MSB_ERR_WORKSPACE, "sort_gaussian: keygen status");
-    keygen_kernel<<<kgrid, KG_NT, 0, st>>>(P, seg, reinterpret_cast<const float2*>(uv), depth, radius, tiles, gx, gy,
+    keygen_kernel<<<kgrid, KG_NT, 0, st>>>(P, max(Pv, 1), seg, reinterpret_cast<const float2*>(uv), depth, radius, tiles, gx, gy,
                                            U32(L.dkeys[0]), I32(L.dvals[0]), reinterpret_cast<int4*>(base + L.rect), hist,
                                            zcount,
                                            U32(L.status_k), ticket + 4 + MAX_TPASS, pcount);
@@ -1001,6 +1060,14 @@ int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     tile_range_kernel<<<(unsigned)((M + 1023) / 1024), 256, 0, st>>>((int)M, tk[L.tpass % 2],
                                                                   reinterpret_cast<int2*>(tile_range), T);
     return check_launch("sort_gaussian/tile_range");
+}
+
+// Phase 2.  idx_sorted[M] (int32) and tile_range[T, 2] (int32) are outputs owned by the caller.
+int msb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles, int P,
+                      long long M, int W, int H, int32_t* idx_sorted, int32_t* tile_range, void* ws, size_t ws_bytes,
+                      int sm_count, void* stream) {
+    return msb_sort_gaussian_views(uv, depth, radius, tiles, P, 1, M, W, H, idx_sorted, tile_range, ws, ws_bytes,
+                                   sm_count, stream);
 }
 
 }  // extern "C"

@@ -9,20 +9,25 @@ The reference only offers this as a chain of steps plus torch glue
     feature = cat(rgb, depth) [optional];  cov3d = compute_cov3d(...);  conic, radius, tiles = ewa_project(...)
     ids, tile_range = sort_gaussian(...);  image = alpha_blending(...)
 
-Here the whole per-Gaussian part is ONE forward and ONE backward kernel (csrc/render.cu) that read
-the parameters once, never materialise cov3d / dirs / rgb and write straight into the blend
-kernels' packed layout; sort and blend are the same kernels as the steps API.  uv, depth, radius,
-tiles, idx_sorted and tile_range are bit-identical to the steps pipeline; images agree to FP32
-rounding of the view-direction normalisation (tests/test_gpu_parity.py::test_render_sh_*).
+Here a whole VIEW BATCH is one virtual scene: B views x P Gaussians are B*P virtual
+Gaussians (id = view * P' + index, P' = P rounded up to 4) on a virtual grid of B*T tiles
+(id = view * T + tile).  Per chunk of views (all B by default) that is
 
-A view batch shares one host sync (all M read-backs at once) and accumulates the per-Gaussian
-gradients of its views inside the backward kernel (no per-view add passes): SURVEY 8f ranks 1+3.
+    1 launch   msb_render_preprocess_fwd_views   parameters + SH rows read once, per-view packed records out
+    1 sort     msb_sort_gaussian_views           (view | tile | depth) keys, one onesweep sort
+    1 launch   msb_blend_packed_fwd_views        blockIdx.z = view
+    1 launch   msb_blend_packed_bwd_views
+    1 launch   msb_render_preprocess_bwd_views   gradients summed over the views in registers / at the L2
+
+instead of B times each.  uv, depth, radius, tiles, the per-view order of idx_sorted and tile_range are
+bit-identical to the steps pipeline; images agree to FP32 rounding of the view-direction normalisation
+(tests/test_gpu_render_sh.py).  One host sync per call (all M read-backs at once).
 """
 from __future__ import annotations
 
-from typing import Tuple
-
 import os
+import threading
+from contextlib import contextmanager
 
 import torch
 from torch import Tensor
@@ -30,29 +35,47 @@ from torch import Tensor
 from . import _lib
 from ._lib import as_f32, ptr
 
-__all__ = ["rasterization_sh", "rasterization_sh_views"]
+__all__ = ["rasterization_sh", "rasterization_sh_views", "serialised"]
 
-# Two-stream schedule for view batches: the sort of view b+1 (latency-bound integer passes) runs on a
-# side stream under the forward blend of view b (issue-bound), and the fused preprocess backward of
-# view b (HBM-bound) under the backward blend of view b+1.  Results are unaffected (same kernels,
-# same accumulation order); set to False to serialise everything on the caller's stream (used by
-# bench.py for per-kernel timings).
+# Two-stream schedule when a view batch is processed in several chunks: the sort of chunk k+1
+# (integer passes) runs on a side stream under the forward blend of chunk k (issue-bound), and the fused
+# preprocess backward of chunk k (HBM-bound) under the backward blend of chunk k+1.  The packed gradient
+# buffers are always cleared on the side stream, under the forward sort/blend.  Results do not depend on it.
+# ``with serialised():`` puts everything on the caller's stream for the calling thread (per-kernel timings).
 OVERLAP = True
-_side_streams = {}
+_tls = threading.local()
+
+# views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
+VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
+M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
 
 
-SORT_STREAMS = int(os.environ.get("MSB_SORT_STREAMS", "1"))  # side streams the sorts of a view batch rotate over
+@contextmanager
+def serialised():
+    prev = getattr(_tls, "serial", False)
+    _tls.serial = True
+    try:
+        yield
+    finally:
+        _tls.serial = prev
 
 
-def _side_stream(dev, k: int = 0) -> "torch.cuda.Stream":
+def _overlap() -> bool:
+    return OVERLAP and not getattr(_tls, "serial", False)
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """Per-thread, per-device side stream (high priority: its CTAs are dispatched as soon as blend CTAs
+    retire instead of queueing behind the thousands of tile CTAs launched before them)."""
     idx = torch.device(dev).index
     if idx is None:
         idx = torch.cuda.current_device()
-    if (idx, k) not in _side_streams:
-        # high priority: its CTAs are dispatched as soon as blend CTAs retire instead of queueing behind the
-        # thousands of tile CTAs of the blend kernel launched before them
-        _side_streams[(idx, k)] = torch.cuda.Stream(device=idx, priority=-1)
-    return _side_streams[(idx, k)]
+    cache = getattr(_tls, "streams", None)
+    if cache is None:
+        cache = _tls.streams = {}
+    if idx not in cache:
+        cache[idx] = torch.cuda.Stream(device=idx, priority=-1)
+    return cache[idx]
 
 
 def rasterization_sh(
@@ -75,54 +98,93 @@ def rasterization_sh(
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3, ndc: Tensor = None,
-    return_aux: bool = False,
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 1, ndc: Tensor = None,
+    return_aux: bool = False, view_chunk: int = None, stats: dict = None,
 ):
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
-    -> images [B,C,H,W].
+    -> images [B,C,H,W].  ``view_chunk``: views per batched launch (default: all B).
 
     Side outputs a 3DGS trainer reads every step, at no extra pass:
     ``ndc`` [B,P,2] is a dummy input whose ``.grad`` receives the screen-space gradient
     ``dL_duv * [0.5 W, 0.5 H]`` of every view (the reference's hook, msplat/alpha_blending.py:107-110,
     which densification heuristics accumulate); ``return_aux=True`` returns
     ``(images, radii [B,P] int32, visible [B,P] bool)`` with ``visible = radii > 0`` (the Gaussians
-    that take part in a view, src/sort_gaussian.cu:26).
+    that take part in a view, src/sort_gaussian.cu:26).  ``stats`` (a dict) receives the cross-view
+    accumulators densification reads: ``max_radii`` [P] int32 (forward) and, after backward,
+    ``ndc_grad_norm_sum`` [P] = sum over views of ||dL_dndc|| and ``ndc_grad_count`` [P] (views in which the
+    Gaussian was visible).
+
+    The gradient w.r.t. ``extrs`` includes the dependence of the view direction on the camera centre
+    (-R^T t), which a steps pipeline only has if it does not detach the centre.
 
     ``grad_sync`` (view-batch data parallelism): a ``torch.distributed`` process group
     (or ``True`` for the default group).  The backward pass then returns the per-Gaussian gradients
-    already SUMMED over the ranks of that group: the Gaussians are processed in ``grad_chunks``
-    slabs, and the all-reduce of a finished slab (NCCL, its own stream) runs under the
-    preprocess-backward kernels of the following slabs instead of after the whole backward.
-    Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a
-    custom reducer: it is called with every finished gradient slab (in place) and may return an
-    object with ``.wait()``."""
+    already SUMMED over the ranks of that group.  Only the rows some rank touched travel: the ranks
+    sum-reduce a per-Gaussian "received a colour gradient" mask (4 B per Gaussian), the fused
+    preprocess backward writes its dL_dshs rows compacted to the union, and ONE flat all-reduce per slab
+    of Gaussians (``grad_chunks`` slabs; a slab's all-reduce runs under the kernels of the next) carries
+    the 11 dense geometry floats plus the compact rows; the result is expanded back to [P,Cs,D].
+    Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a custom
+    reducer: it is called in place with the int32 mask [P] and with every flat float32 slab (sum
+    semantics) and may return an object with ``.wait()``."""
     if intrs.dim() == 1:
         intrs = intrs[None].expand(extrs.shape[0], 4)
     if ndc is not None and tuple(ndc.shape) != (extrs.shape[0], xyz.shape[0], 2):
         raise RuntimeError("rasterization_sh_views: ndc must be [B, P, 2]")
+    vc = VIEW_CHUNK if view_chunk is None else int(view_chunk)
     images, radii = _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
                                          float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent),
-                                         grad_sync, int(grad_chunks), ndc, bool(return_aux))
+                                         grad_sync, int(grad_chunks), ndc, bool(return_aux), vc, stats)
     if return_aux:
         return images, radii, radii > 0
     return images
 
 
 def _resolve_group(grad_sync):
-    """-> process group to all-reduce over, or None when there is nothing to do."""
+    """-> process group to all-reduce over, a custom reducer, or None when there is nothing to do."""
     import torch.distributed as dist
     if callable(grad_sync):
-        return grad_sync  # custom reducer: called as grad_sync(tensor_slab) -> None | object with .wait()
+        return grad_sync  # custom reducer: called as grad_sync(tensor) -> None | object with .wait()
     if grad_sync is None or grad_sync is False or not (dist.is_available() and dist.is_initialized()):
         return None
     group = dist.group.WORLD if grad_sync is True else grad_sync
     return group if dist.get_world_size(group) > 1 else None
 
 
+def _reduce(group, t, async_op=False):
+    """sum-reduce `t` in place over the group (or through the custom reducer)"""
+    if callable(group):
+        return group(t)
+    import torch.distributed as dist
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def _chunks(B, vc):
+    vc = B if vc <= 0 else min(vc, B)
+    return [(b0, min(vc, B - b0)) for b0 in range(0, B, vc)]
+
+
+def _split_for_sort(chunks, Ms):
+    """Chunks whose views hold more than 2^31 - 1 tile intersections together are split (greedily)."""
+    out = []
+    for b0, nb in chunks:
+        start, acc = b0, 0
+        for b in range(b0, b0 + nb):
+            if Ms[b] > M_MAX:
+                raise RuntimeError(f"rasterization_sh: view {b} has {Ms[b]} tile intersections, more than the "
+                                   f"supported 2^31 - 1 (int32 positions, like the reference's int32 cumsum)")
+            if acc + Ms[b] > M_MAX:
+                out.append((start, b - start))
+                start, acc = b, 0
+            acc += Ms[b]
+        out.append((start, b0 + nb - start))
+    return out
+
+
 class _RenderSHViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scale, rotate, opacity, shs, intrs, extrs, W, H, bg, sh_bias, clamp, with_depth, nearest,
-                extent, grad_sync, grad_chunks, ndc, return_aux):
+                extent, grad_sync, grad_chunks, ndc, return_aux, view_chunk, stats):
         x, s, q = as_f32(xyz, "xyz"), as_f32(scale, "scale"), as_f32(rotate, "rotate")
         o, sh = as_f32(opacity, "opacity"), as_f32(shs, "shs")
         I, E = as_f32(intrs, "intrs"), as_f32(extrs, "extrs")
@@ -137,188 +199,249 @@ class _RenderSHViews(torch.autograd.Function):
         if E.dim() != 3 or E.shape[1] not in (3, 4) or E.shape[2] != 4 or I.shape != (E.shape[0], 4):
             raise RuntimeError("rasterization_sh_views: intrs [B,4], extrs [B,3,4] or [B,4,4]")
         B = E.shape[0]
+        es = int(E.shape[1]) * 4  # floats between consecutive extrinsics
         C = Cs + (1 if with_depth else 0)
         dev = x.device
         L = _lib.lib()
         cpad = L.msb_blend_cpad(C)
         T = ((W + 15) // 16) * ((H + 15) // 16)
+        Pp = (P + 3) // 4 * 4  # rows per view of the view-major buffers: keeps every view's slabs 16-byte aligned
+        chunks = _chunks(B, view_chunk)
+        if max(nb for _, nb in chunks) * max(Pp, T) > M_MAX:
+            raise RuntimeError("rasterization_sh_views: views per chunk x Gaussians (or tiles) must stay below 2^31; "
+                               "pass a smaller view_chunk")
         f32, i32 = torch.float32, torch.int32
-        images = torch.empty((B, C, H, W), dtype=f32, device=dev)
-        views = []
+        need_grad = any(ctx.needs_input_grad[:7])
         with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            images = torch.empty((B, C, H, W), dtype=f32, device=dev)
+            rec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
+            featp = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
+            uv = torch.empty((B, Pp, 2), dtype=f32, device=dev)
+            depth = torch.empty((B, Pp), dtype=f32, device=dev)
+            radius = torch.empty((B, Pp), dtype=i32, device=dev)
+            tiles = torch.empty((B, Pp), dtype=i32, device=dev)
+            if Pp != P:  # padding rows take no part in the sort
+                tiles[:, P:].zero_()
+                radius[:, P:].zero_()
+            final_T = torch.empty((B, H, W), dtype=f32, device=dev)
+            ncontrib = torch.empty((B, H, W), dtype=i32, device=dev)
+            tr = torch.empty((B * T, 2), dtype=i32, device=dev)
             totals = _lib.pinned_i64(dev, B)
             total_dev = torch.empty((B,), dtype=torch.int64, device=dev)
-            # phase A: per-Gaussian preprocess + tile-count scan of every view, then ONE host sync
-            for b in range(B):
-                rec = torch.empty((P, 8), dtype=f32, device=dev)
-                featp = torch.empty((P, cpad), dtype=f32, device=dev)
-                uv = torch.empty((P, 2), dtype=f32, device=dev)
-                depth = torch.empty((P,), dtype=f32, device=dev)
-                radius = torch.empty((P,), dtype=i32, device=dev)
-                tiles = torch.empty((P,), dtype=i32, device=dev)
-                # M = sum(tiles) of view b is accumulated by the same kernel into total_dev[b]
-                _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd, dev, ptr(x), ptr(s),
-                          ptr(q), ptr(o), ptr(sh), ptr(I[b]), ptr(E[b]), P, Cs, D, int(with_depth), W, H, nearest,
-                          extent, sh_bias, int(clamp), ptr(rec), ptr(featp), ptr(uv), ptr(depth), ptr(radius),
-                          ptr(tiles), ptr(total_dev[b:]), None)
-                views.append([rec, featp, uv, depth, radius, tiles])
-            totals[:B].copy_(total_dev, non_blocking=True)  # one device->host copy for the whole batch
-            main = torch.cuda.current_stream(dev)
-            main.synchronize()
-            Ms = [int(totals[b]) for b in range(B)]
-            sides = [_side_stream(dev, k) for k in range(max(1, SORT_STREAMS))] if (OVERLAP and B > 1) else None
-            if sides is not None:
-                for st_ in sides[1:]:
-                    st_.wait_stream(main)  # the per-view tensors were produced on `main`
-            # phase B: sort (side stream when overlapping) + blend (caller's stream) per view
-            saved, keep = [], []
-            radii = torch.stack([v[4] for v in views]) if return_aux else torch.empty((0,), dtype=i32, device=dev)
-            for b in range(B):
-                rec, featp, uv, depth, radius, tiles = views[b]
-                M = Ms[b]
-                if M >= 2 ** 30:
-                    raise RuntimeError(f"rasterization_sh: {M} tile intersections exceed the supported 2^30")
-                ids = torch.empty((M,), dtype=i32, device=dev)
-                tr = torch.empty((T, 2), dtype=i32, device=dev)
-                ws2 = torch.empty((L.msb_sort_workspace_bytes(P, M, W, H),), dtype=torch.uint8, device=dev)
-                final_T = torch.empty((H, W), dtype=f32, device=dev)
-                ncontrib = torch.empty((H, W), dtype=i32, device=dev)
-                nk = 4 + L.msb_sort_num_passes(W, H) if (M > 0 and P > 0) else 0  # keygen, offsets, duplicate, ranges + passes
-                side = sides[b % len(sides)] if sides is not None else None
+            side = _side_stream(dev) if _overlap() else None
+            grec = gfeat = cleared = None
+            if need_grad and P > 0 and C > 0:
+                # packed gradient buffers of the backward blend: cleared now, on the side stream, under the
+                # sort / forward blend (the 48 B per Gaussian and view memset leaves the critical path)
+                grec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
+                gfeat = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
                 with torch.cuda.stream(side if side is not None else main):
-                    _lib.call("sort_gaussian", nk, L.msb_sort_gaussian, dev, ptr(uv), ptr(depth), ptr(radius),
-                              ptr(tiles), P, M, W, H, ptr(ids), ptr(tr), ptr(ws2), ws2.numel(), _lib.sm_count(dev))
                     if side is not None:
+                        side.wait_stream(main)
+                    grec.zero_()
+                    gfeat.zero_()
+                    cleared = side.record_event() if side is not None else None
+            # phase A: per-Gaussian preprocess of every chunk (M per view accumulated in-kernel), ONE host sync
+            for b0, nb in chunks:
+                _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd_views, dev, ptr(x),
+                          ptr(s), ptr(q), ptr(o), ptr(sh), ptr(I[b0]), ptr(E[b0]), es, P, nb, Pp, Cs, D,
+                          int(with_depth), W, H, nearest, extent, sh_bias, int(clamp), ptr(rec[b0]), ptr(featp[b0]),
+                          ptr(uv[b0]), ptr(depth[b0]), ptr(radius[b0]), ptr(tiles[b0]), ptr(total_dev[b0:]))
+            totals[:B].copy_(total_dev, non_blocking=True)  # one device->host copy for the whole batch
+            done = main.record_event()
+            done.synchronize()
+            Ms = [int(totals[b]) for b in range(B)]
+            chunks = _split_for_sort(chunks, Ms)  # raises before anything else is queued
+            # phase B: one sort (side stream when several chunks overlap) + one blend grid per chunk
+            two_stream = side is not None and len(chunks) > 1
+            if two_stream:
+                side.wait_stream(main)  # the per-view tensors were produced on `main`
+            ids_all, keep = [], []
+            for b0, nb in chunks:
+                M = sum(Ms[b0:b0 + nb])
+                ids = torch.empty((M,), dtype=i32, device=dev)
+                ws2 = torch.empty((L.msb_sort_workspace_bytes_views(Pp, nb, M, W, H),), dtype=torch.uint8, device=dev)
+                nk = L.msb_sort_num_passes_views(W, H, nb) + 4 if (M > 0 and P > 0) else 0  # + keygen, offsets, duplicate, ranges
+                with torch.cuda.stream(side if two_stream else main):
+                    _lib.call("sort_gaussian", nk, L.msb_sort_gaussian_views, dev, ptr(uv[b0]), ptr(depth[b0]),
+                              ptr(radius[b0]), ptr(tiles[b0]), Pp, nb, M, W, H, ptr(ids), ptr(tr[b0 * T:]), ptr(ws2),
+                              ws2.numel(), _lib.sm_count(dev))
+                    if two_stream:
                         main.wait_event(side.record_event())
-                _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd, dev, ptr(rec), ptr(featp),
-                          ptr(ids), ptr(tr), bg, C, W, H, ptr(images[b]), ptr(final_T), ptr(ncontrib))
-                saved += [rec, featp, tiles, ids, tr, final_T, ncontrib]
-                keep += [uv, depth, radius, ws2]  # alive until both streams are joined (allocated on `main`)
-                views[b] = None
-            # all side-stream work is ordered before the last blend, hence before anything the caller enqueues next
-            del keep
-        ctx.cfg = (B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth)
+                _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd_views, dev, ptr(rec[b0]),
+                          ptr(featp[b0]), ptr(ids), ptr(tr[b0 * T:]), bg, C, W, H, nb, ptr(images[b0]),
+                          ptr(final_T[b0]), ptr(ncontrib[b0]))
+                ids_all.append(ids)
+                keep.append(ws2)  # alive until both streams are joined (allocated on `main`)
+            # all side-stream sorts are ordered before the last blend, hence before anything the caller enqueues
+            del keep, uv, depth
+            radii = radius[:, :P] if return_aux else torch.empty((0,), dtype=i32, device=dev)
+            if stats is not None:
+                stats["max_radii"] = radius[:, :P].amax(dim=0) if B > 0 else torch.zeros(P, dtype=i32, device=dev)
+        ctx.cfg = (B, P, Pp, Cs, D, C, cpad, W, H, T, es, bg, sh_bias, clamp, with_depth)
+        ctx.chunks = chunks
         ctx.cam_grad = (intrs.requires_grad, extrs.requires_grad)
         ctx.grad_sync = (grad_sync, grad_chunks)
         ctx.shapes = (tuple(opacity.shape), tuple(intrs.shape), tuple(extrs.shape))
         ctx.has_ndc = ndc is not None
-        ctx.save_for_backward(x, s, q, sh, I, E, *saved)
+        ctx.stats = stats
+        ctx.gbuf = (grec, gfeat, cleared)
+        ctx.gclean = True
+        ctx.save_for_backward(x, s, q, sh, I, E, rec, featp, tiles, tr, final_T, ncontrib, *ids_all)
         ctx.mark_non_differentiable(radii)
         return images, radii
 
     @staticmethod
     def backward(ctx, dL_dimages, _dL_dradii=None):
-        B, P, Cs, D, C, cpad, W, H, bg, sh_bias, clamp, with_depth = ctx.cfg
-        x, s, q, sh, I, E = ctx.saved_tensors[:6]
-        saved = ctx.saved_tensors[6:]
+        B, P, Pp, Cs, D, C, cpad, W, H, T, es, bg, sh_bias, clamp, with_depth = ctx.cfg
+        x, s, q, sh, I, E, rec, featp, tiles, tr, final_T, ncontrib = ctx.saved_tensors[:12]
+        ids_all = ctx.saved_tensors[12:]
+        chunks = ctx.chunks
         g = as_f32(dL_dimages, "dL_dimages")
         dev = x.device
         L = _lib.lib()
-        f32 = torch.float32
-        dxyz = torch.empty((P, 3), dtype=f32, device=dev)
-        dscale = torch.empty((P, 3), dtype=f32, device=dev)
-        dquat = torch.empty((P, 4), dtype=f32, device=dev)
-        dop = torch.empty((P,), dtype=f32, device=dev)
-        dshs = torch.empty_like(sh)
+        f32, i32 = torch.float32, torch.int32
         need_i, need_e = ctx.cam_grad
-        # screen-space gradient hook: dL_duv of view b is columns 0:2 of its packed gradient record
-        dndc = torch.zeros((B, P, 2), dtype=f32, device=dev) if ctx.has_ndc else None
-        ndc_scale = torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev) if ctx.has_ndc else None
         dintr = torch.zeros((B, 4), dtype=f32, device=dev) if need_i else None
-        dextr = torch.zeros((B,) + tuple(E.shape[1:]), dtype=f32, device=dev) if need_e else None
-        if P == 0 or C == 0:
-            for t in (dxyz, dscale, dquat, dop, dshs):
-                t.zero_()
-        else:
-            group = _resolve_group(ctx.grad_sync[0])
-            outs = (dxyz, dscale, dquat, dop, dshs)
-
-            def pre_bwd(b, gr, gf, lo, hi):
-                """fused preprocess backward of view b for the Gaussians [lo, hi) (accumulates for b > 0)"""
-                _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd, dev, ptr(x[lo:hi]),
-                          ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[b]), ptr(E[b]), ptr(saved[7 * b + 2][lo:hi]),
-                          ptr(gr[lo:hi]), ptr(gf[lo:hi]), hi - lo, Cs, D, int(with_depth), sh_bias, int(clamp),
-                          1 if b > 0 else 0, ptr(dxyz[lo:hi]), ptr(dscale[lo:hi]), ptr(dquat[lo:hi]), ptr(dop[lo:hi]),
-                          ptr(dshs[lo:hi]), ptr(dintr[b]) if need_i else None, ptr(dextr[b]) if need_e else None)
-
-            def blend_bwd(b, gr, gf, already_zero=False):
-                rec, featp, tiles, ids, tr, final_T, ncontrib = saved[7 * b:7 * b + 7]
-                _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd, dev, ptr(rec),
-                          ptr(featp), ptr(ids), ptr(tr), bg, P, C, W, H, ptr(final_T), ptr(ncontrib), ptr(g[b]),
-                          ptr(gr), ptr(gf), int(already_zero))
-
-            with torch.cuda.device(dev):
-                main = torch.cuda.current_stream(dev)
-                if group is not None:
-                    # data-parallel schedule: all blend backwards first (packed gradients kept per view), then
-                    # the preprocess backward slab by slab; a finished slab is all-reduced while the next runs
-                    import torch.distributed as dist
-                    grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(B)]
-                    gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(B)]
-                    # the packed gradient buffers are cleared on the side stream, under the backward blends of
-                    # the views before (only the first blend waits for its clear)
-                    side = _side_stream(dev) if OVERLAP else None
-                    cleared = [None] * B
-                    if side is not None:
-                        side.wait_stream(main)
-                        with torch.cuda.stream(side):
-                            for b in range(B):
-                                grec[b].zero_()
-                                gfeat[b].zero_()
-                                cleared[b] = side.record_event()
-                    for b in range(B):
-                        if side is not None:
-                            main.wait_event(cleared[b])
-                        blend_bwd(b, grec[b], gfeat[b], already_zero=side is not None)
-                        if dndc is not None:
-                            torch.mul(grec[b][:, :2], ndc_scale, out=dndc[b])
-                    nchunk = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
-                    step = ((P + nchunk - 1) // nchunk + 255) // 256 * 256  # slab starts stay 16-byte aligned
-                    works = []
-                    for lo in range(0, P, step):
-                        hi = min(P, lo + step)
-                        for b in range(B):
-                            pre_bwd(b, grec[b], gfeat[b], lo, hi)
-                        for t in outs:
-                            if callable(group):
-                                works.append(group(t[lo:hi]))
-                            else:
-                                works.append(dist.all_reduce(t[lo:hi], op=dist.ReduceOp.SUM, group=group,
-                                                             async_op=True))
-                    for w in works:
-                        if w is not None:
-                            w.wait()
-                else:
-                    side = _side_stream(dev) if (OVERLAP and B > 1) else None
-                    nbuf = 2 if side is not None else 1
-                    grec = [torch.empty((P, 8), dtype=f32, device=dev) for _ in range(nbuf)]
-                    gfeat = [torch.empty((P, cpad), dtype=f32, device=dev) for _ in range(nbuf)]
-                    done = [None] * B
-                    if side is not None:
-                        side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
-                    for b in range(B):
-                        k = b % nbuf
-                        if side is not None and b >= nbuf:
-                            main.wait_event(done[b - nbuf])  # the packed-gradient buffer is free again
-                        # from the third view on the buffer was cleared on the side stream (below), under the
-                        # backward blend of the view before: the 144 MB memset leaves the critical path
-                        blend_bwd(b, grec[k], gfeat[k], already_zero=(side is not None and b >= nbuf))
-                        if dndc is not None:  # on `main`, before blend_bwd(b + nbuf) rewrites the buffer
-                            torch.mul(grec[k][:, :2], ndc_scale, out=dndc[b])
-                        with torch.cuda.stream(side if side is not None else main):
-                            if side is not None:
-                                side.wait_event(main.record_event())
-                            pre_bwd(b, grec[k], gfeat[k], 0, P)
-                            if side is not None:
-                                if b + nbuf < B:
-                                    grec[k].zero_()
-                                    gfeat[k].zero_()
-                                done[b] = side.record_event()
-                    if side is not None:
-                        main.wait_stream(side)
+        dextr = torch.zeros((B, es), dtype=f32, device=dev) if need_e else None
+        dndc = None
         op_shape = ctx.shapes[0]
-        return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr, dextr, None, None, None, None, None, None,
-                None, None, None, None, dndc, None)
+        if P == 0 or C == 0:
+            z = lambda *shape: torch.zeros(shape, dtype=f32, device=dev)
+            if ctx.has_ndc:
+                dndc = z(B, P, 2)
+            return (z(P, 3), z(P, 3), z(P, 4), z(*op_shape), torch.zeros_like(sh), dintr,
+                    None if dextr is None else dextr.reshape(ctx.shapes[2]), None, None, None, None, None, None, None,
+                    None, None, None, dndc, None, None, None)
+        group = _resolve_group(ctx.grad_sync[0])
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            grec, gfeat, cleared = ctx.gbuf
+            if grec is None:
+                grec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
+                gfeat = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
+                ctx.gclean = False
+            if not ctx.gclean:  # a second backward through the same graph (retain_graph=True)
+                grec.zero_()
+                gfeat.zero_()
+            elif cleared is not None:
+                main.wait_event(cleared)
+            ctx.gclean = False
+
+            def blend_bwd(k):
+                b0, nb = chunks[k]
+                _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd_views, dev, ptr(rec[b0]),
+                          ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[b0 * T:]), bg, Pp, C, W, H, nb, ptr(final_T[b0]),
+                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
+
+            def pre_bwd(k, lo, hi, accumulate, outs, row_index=None, row_base=0):
+                """fused preprocess backward of chunk k for the Gaussians [lo, hi)"""
+                b0, nb = chunks[k]
+                dxyz, dscale, dquat, dop, dshs = outs
+                _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd_views, dev, ptr(x[lo:hi]),
+                          ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[b0]), ptr(E[b0]), es,
+                          ptr(tiles[b0, lo:]), ptr(grec[b0, lo:]), ptr(gfeat[b0, lo:]),
+                          None if row_index is None else ptr(row_index[lo:hi]), row_base, hi - lo, nb, Pp, Cs, D,
+                          int(with_depth), sh_bias, int(clamp), int(accumulate), ptr(dxyz), ptr(dscale), ptr(dquat),
+                          ptr(dop), ptr(dshs), ptr(dintr[b0]) if need_i else None, ptr(dextr[b0]) if need_e else None)
+
+            if group is None:
+                dxyz = torch.empty((P, 3), dtype=f32, device=dev)
+                dscale = torch.empty((P, 3), dtype=f32, device=dev)
+                dquat = torch.empty((P, 4), dtype=f32, device=dev)
+                dop = torch.empty((P,), dtype=f32, device=dev)
+                dshs = torch.empty_like(sh)
+                outs = (dxyz, dscale, dquat, dop, dshs)
+                side = _side_stream(dev) if (_overlap() and len(chunks) > 1) else None
+                if side is not None:
+                    side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
+                for k in range(len(chunks)):
+                    blend_bwd(k)
+                    with torch.cuda.stream(side if side is not None else main):
+                        if side is not None:
+                            side.wait_event(main.record_event())
+                        pre_bwd(k, 0, P, k > 0, outs)
+                if side is not None:
+                    main.wait_stream(side)
+            else:
+                dxyz, dscale, dquat, dop, dshs = _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev)
+            gr = grec[:, :P]
+            if ctx.has_ndc:  # screen-space gradient hook: dL_duv of view b is columns 0:2 of its packed record
+                dndc = gr[:, :, :2] * torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev)
+            if ctx.stats is not None:
+                nd = gr[:, :, :2] * torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev)
+                ctx.stats["ndc_grad_norm_sum"] = nd.norm(dim=-1).sum(dim=0)
+                ctx.stats["ndc_grad_count"] = (tiles[:, :P] > 0).sum(dim=0).to(i32)
+        return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr,
+                None if dextr is None else dextr.reshape(ctx.shapes[2]), None, None, None, None, None, None, None, None,
+                None, None, dndc, None, None, None)
+
+
+def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
+    """View-batch data parallelism: every rank renders its own views; the per-Gaussian gradients are summed
+    over the ranks.  Only rows that some rank touched are sent (see rasterization_sh_views)."""
+    B, P, Pp, Cs, D, C, cpad = ctx.cfg[:7]
+    chunks = ctx.chunks
+    L = _lib.lib()
+    f32, i32 = torch.float32, torch.int32
+    main = torch.cuda.current_stream(dev)
+    for k in range(len(chunks)):
+        blend_bwd(k)
+    # 1. which Gaussians received a colour gradient on this rank -> summed over the ranks (> 0 = union)
+    mask = torch.empty((P,), dtype=i32, device=dev)
+    _lib.call("grad_live_mask", 1, L.msb_grad_live_mask, dev, ptr(gfeat), P, B, Pp, cpad, ptr(mask))
+    w = _reduce(group, mask)
+    if w is not None and hasattr(w, "wait"):
+        w.wait()
+    # 2. compact row of every Gaussian of the union; U and the slab boundaries go to the host
+    nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
+    step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
+    bounds = [(lo, min(P, lo + step)) for lo in range(0, P, step)]
+    incl = torch.empty((P,), dtype=i32, device=dev)
+    row_index = torch.empty((P,), dtype=i32, device=dev)
+    ws = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
+    total = _lib.pinned_i64(dev, len(bounds) + 1)
+    _lib.call("grad_row_index", 4, L.msb_grad_row_index, dev, ptr(mask), P, ptr(incl), ptr(row_index), ptr(total),
+              ptr(ws), ws.numel())
+    ends = incl[torch.tensor([hi - 1 for _, hi in bounds], device=dev)].to(torch.int64)
+    total[1:1 + len(bounds)].copy_(ends, non_blocking=True)
+    main.record_event().synchronize()
+    cum = [0] + [int(total[1 + k]) for k in range(len(bounds))]
+    # 3. per slab: one flat buffer [dxyz | dscale | dquat | dopacity | compact dL_dshs rows], one all-reduce
+    F = Cs * D
+    works, slabs = [], []
+    for k, (lo, hi) in enumerate(bounds):
+        n, u = hi - lo, cum[k + 1] - cum[k]
+        n4 = (n + 3) // 4 * 4
+        flat = torch.empty((11 * n4 + u * F,), dtype=f32, device=dev)
+        outs = (flat[0:3 * n].view(n, 3), flat[3 * n4:3 * n4 + 3 * n].view(n, 3),
+                flat[6 * n4:6 * n4 + 4 * n].view(n, 4), flat[10 * n4:10 * n4 + n], flat[11 * n4:].view(u, F))
+        if n4 != n:
+            flat[:11 * n4].zero_()  # the few padding floats are reduced too
+        for c in range(len(chunks)):
+            pre_bwd(c, lo, hi, c > 0, outs, row_index, cum[k])
+        works.append(_reduce(group, flat, async_op=True))
+        slabs.append((lo, hi, outs))
+    # 4. wait, then expand the compact rows back to [P, Cs, D]
+    dxyz = torch.empty((P, 3), dtype=f32, device=dev)
+    dscale = torch.empty((P, 3), dtype=f32, device=dev)
+    dquat = torch.empty((P, 4), dtype=f32, device=dev)
+    dop = torch.empty((P,), dtype=f32, device=dev)
+    dshs = torch.empty_like(sh)
+    for k, (lo, hi, outs) in enumerate(slabs):
+        if works[k] is not None and hasattr(works[k], "wait"):
+            works[k].wait()
+        dxyz[lo:hi].copy_(outs[0])
+        dscale[lo:hi].copy_(outs[1])
+        dquat[lo:hi].copy_(outs[2])
+        dop[lo:hi].copy_(outs[3])
+        _lib.call("grad_expand_rows", 1, L.msb_grad_expand_rows, dev, ptr(outs[4]), ptr(row_index[lo:hi]), cum[k],
+                  hi - lo, F, ptr(dshs[lo:hi]))
+    if ctx.stats is not None:
+        ctx.stats["allreduce_floats"] = sum(int(o[4].numel()) + 11 * (hi - lo) for lo, hi, o in slabs)
+        ctx.stats["allreduce_dense_floats"] = P * (11 + F)
+    return dxyz, dscale, dquat, dop, dshs
 
 
 def _blend_passes_fwd(cpad: int, C: int) -> int:

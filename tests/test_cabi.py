@@ -24,7 +24,8 @@ def test_public_api_names_match_reference():
     ref_names = {"project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "compute_sh", "alpha_blending",
                  "rasterization"}
     assert ref_names <= set(msplat_b200.__all__)
-    assert set(msplat_b200.__all__) - ref_names == {"rasterization_sh", "rasterization_sh_views"}  # extensions
+    assert set(msplat_b200.__all__) - ref_names == {"rasterization_sh", "rasterization_sh_views",
+                                                    "sort_gaussian_views"}  # extensions
     import inspect
     sig = inspect.signature(msplat_b200.project_point)
     assert list(sig.parameters) == ["xyz", "intr", "extr", "W", "H", "nearest", "extent"]

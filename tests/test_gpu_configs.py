@@ -3,14 +3,14 @@ here against the unmodified reference CUDA build on identical inputs, at the nam
 size that runs in seconds, plus size-independent properties at the full size).
 
 Bars: sort outputs / tiles_touched / radius bit-exact; images max abs 1e-4 x max(1, |image|);
-gradients |d| <= rel |g| + eps max|g|.
+gradients |d| <= 1e-3 |g| + K_NOISE x (the reference's measured run-to-run spread), see test_gpu_parity.
 """
 import math
 
 import pytest
 import torch
 
-from test_gpu_parity import DEV, grad_close
+from test_gpu_parity import DEV, compare_grads, grad_close, spread
 from test_gpu_render_sh import steps_pipeline
 
 pytestmark = pytest.mark.gpu
@@ -42,16 +42,22 @@ def test_config2_bunny2d_init_vs_reference(ms, ref_msplat):
     assert ours[5].numel() > 30_000_000
     rgb = torch.sigmoid(torch.rand(sc.xyz.shape[0], 3, generator=torch.Generator().manual_seed(1))).to(DEV)
     mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, rgb)]
-    A, B = mk(), mk()
-    img = ms.rasterization(*A, sc.intr, sc.extr, sc.W, sc.H, 1.0)
-    img_r = ref_msplat.rasterization(*B, sc.intr, sc.extr, sc.W, sc.H, 1.0)
-    err = float((img.detach() - img_r.detach()).abs().max())
-    assert err <= 1e-4, f"image max abs error vs reference {err}"
     target = torch.rand(3, sc.H, sc.W, generator=torch.Generator().manual_seed(2)).to(DEV)
-    torch.nn.functional.smooth_l1_loss(img, target).backward()      # the tutorial's loss (gs_2d.py:75)
-    torch.nn.functional.smooth_l1_loss(img_r, target).backward()
-    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "rgb"], A, B):
-        grad_close(a.grad, b.grad, rel=5e-3, eps=1e-3, what=f"config2 d{n}")
+    out = {}
+
+    def run(api):
+        L = mk()
+        img = api.rasterization(*L, sc.intr, sc.extr, sc.W, sc.H, 1.0)
+        out[api] = img.detach()
+        torch.nn.functional.smooth_l1_loss(img, target).backward()      # the tutorial's loss (gs_2d.py:75)
+        return [t.grad for t in L]
+
+    # 64k-entry tile lists: every Gaussian's gradient is a sum over ~1e5 pixel pairs accumulated with float
+    # atomics in the reference (alpha_blending.cu:218-243) -- the measured spread is what "equal" can mean
+    compare_grads(lambda: run(ms), lambda: run(ref_msplat), ["dxyz", "dscale", "dquat", "dopacity", "drgb"],
+                  "config2 init/ref")
+    err = float((out[ms] - out[ref_msplat]).abs().max())
+    assert err <= 1e-4, f"image max abs error vs reference {err}"
 
 
 def test_config2_bunny2d_training_steps_track_reference(ms, ref_msplat):
@@ -89,22 +95,52 @@ def test_config4_high_order_sh_wide_features_vs_reference(ms, ref_msplat):
     steps API of both libraries, and our fused path on the same scene."""
     from msplat_b200.scenes import frustum_scene
     sc = frustum_scene(30000, 1280, 720, 3.0, seed=6, sh_degree=10, sh_channels=32).to(DEV)
+    _config4_compare(ms, ref_msplat, sc, "config4[30k,720p]")
+
+
+def _config4_compare(ms, ref_msplat, sc, tag, fused=True):
     mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
-    A, B, F = mk(), mk(), mk()
-    img = steps_pipeline(ms, A, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)
-    img_r = steps_pipeline(ref_msplat, B, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)
-    img_f = ms.rasterization_sh(*F, sc.intr, sc.extr, sc.W, sc.H, 0.0)
-    assert img.shape == (32, sc.H, sc.W)
-    scale = max(1.0, float(img_r.detach().abs().max()))
-    for name, x in (("steps", img), ("fused", img_f)):
-        err = float((x.detach() - img_r.detach()).abs().max())
+    C = int(sc.shs.shape[1])
+    g = torch.randn(C, sc.H, sc.W, device=DEV)
+    out = {}
+
+    def run(key, fn):
+        L = mk()
+        img = fn(L)
+        out[key] = img.detach()
+        (img * g).sum().backward()
+        grads = [t.grad for t in L]
+        del L, img
+        return grads
+
+    names = ["dxyz", "dscale", "dquat", "dopacity", "dshs"]
+    ref, nf = spread(lambda: run("ref", lambda L: steps_pipeline(ref_msplat, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)), n=1)
+    ours = run("steps", lambda L: steps_pipeline(ms, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False))
+    for n, a, b, f in zip(names, ours, ref, nf):
+        grad_close(a, b, noise=f, what=f"{tag} steps {n}")
+    del ours
+    if fused:
+        ours = run("fused", lambda L: ms.rasterization_sh(*L, sc.intr, sc.extr, sc.W, sc.H, 0.0))
+        for n, a, b, f in zip(names, ours, ref, nf):
+            grad_close(a, b, noise=f, what=f"{tag} fused {n}")
+        del ours
+    assert out["steps"].shape == (C, sc.H, sc.W)
+    scale = max(1.0, float(out["ref"].abs().max()))
+    for name in ("steps", "fused") if fused else ("steps",):
+        err = float((out[name] - out["ref"]).abs().max())
         assert err <= 1e-4 * scale, f"{name}: image max abs error vs reference {err}"
-    g = torch.randn(32, sc.H, sc.W, device=DEV)
-    for x in (img, img_r, img_f):
-        (x * g).sum().backward()
-    for n, a, b, f in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B, F):
-        grad_close(a.grad, b.grad, rel=5e-3, eps=5e-4, what=f"config4 steps d{n}")
-        grad_close(f.grad, b.grad, rel=5e-3, eps=5e-4, what=f"config4 fused d{n}")
+
+
+def test_config4_full_size_64bit_indexing_vs_reference(ms, ref_msplat):
+    """BASELINE config #4 at a size whose SH tensor has more than 2^31 elements: 600k Gaussians x
+    32 channels x 121 coefficients = 2.32e9 floats (9.3 GB) -- every SH index must be 64-bit.  Steps API of
+    both libraries and our fused path on identical tensors, 1080p."""
+    from msplat_b200.scenes import frustum_scene
+    sc = frustum_scene(600_000, 1920, 1080, 2.0, seed=0, sh_degree=10, sh_channels=32).to(DEV)
+    assert sc.shs.numel() > 2 ** 31
+    _config4_compare(ms, ref_msplat, sc, "config4[600k,1080p,>2^31]")
+    del sc
+    torch.cuda.empty_cache()
 
 
 def test_config5_4k_view_batch_vs_reference(ms, ref_msplat):
@@ -114,7 +150,7 @@ def test_config5_4k_view_batch_vs_reference(ms, ref_msplat):
     sc = frustum_scene(400000, 3840, 2160, 3.0, seed=8, sh_degree=3).to(DEV)
     extrs = torch.stack([orbit_cameras(64)[k] for k in (0, 63)]).to(DEV)
     mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
-    A, B = mk(), mk()
+    A = mk()
     imgs = ms.rasterization_sh_views(*A, sc.intr, extrs, sc.W, sc.H, 0.0, with_depth=True)
     g = torch.randn(2, 4, sc.H, sc.W, device=DEV)
     (imgs * g).sum().backward()
@@ -125,13 +161,58 @@ def test_config5_4k_view_batch_vs_reference(ms, ref_msplat):
         ours, ref = _geometry(ms, sk), _geometry(ref_msplat, sk)
         for name, a, b in zip(["uv", "depth", "conic", "radius", "tiles", "idx_sorted", "tile_range"], ours, ref):
             assert torch.equal(a, b), f"view {k}: {name} differs from the reference"
-        img_r = steps_pipeline(ref_msplat, B, sc.intr, extrs[k], sc.W, sc.H, 0.0, True)
-        scale = max(1.0, float(img_r.detach().abs().max()))
-        err = float((imgs[k].detach() - img_r.detach()).abs().max())
-        assert err <= 1e-4 * scale, f"view {k}: image max abs error vs reference {err}"
-        (img_r * g[k]).sum().backward()
-    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "shs"], A, B):
-        grad_close(a.grad, b.grad, rel=5e-3, eps=5e-4, what=f"config5 d{n}")
+
+    def run_ref():
+        B = mk()
+        for k in range(2):
+            img_r = steps_pipeline(ref_msplat, B, sc.intr, extrs[k], sc.W, sc.H, 0.0, True)
+            scale = max(1.0, float(img_r.detach().abs().max()))
+            err = float((imgs[k].detach() - img_r.detach()).abs().max())
+            assert err <= 1e-4 * scale, f"view {k}: image max abs error vs reference {err}"
+            (img_r * g[k]).sum().backward()
+        return [t.grad for t in B]
+
+    ref, nf = spread(run_ref, n=1)
+    for n, a, b, f in zip(["xyz", "scale", "quat", "opacity", "shs"], A, ref, nf):
+        grad_close(a.grad, b, noise=f, what=f"config5 d{n}")
+
+
+def test_config3_full_size_vs_reference(ms, ref_msplat):
+    """The headline configuration at FULL size (3M Gaussians, 1920x1080, SH3, RGB+depth): our fused view
+    batch (2 views, one launch per stage) against the unmodified reference build's steps API on identical
+    tensors -- tiles_touched / radius / idx_sorted / tile_range bit-exact per view, image max abs 1e-4
+    (x the depth channel's scale), gradients within 1e-3 |g| + K_NOISE x the reference's own spread."""
+    from msplat_b200.scenes import frustum_scene, orbit_cameras
+    sc = frustum_scene(3_000_000, 1920, 1080, 2.0, seed=0, sh_degree=3).to(DEV)
+    extrs = torch.stack([e for e in orbit_cameras(8, yaw_deg=20.0, shift=1.0)[:2]]).to(DEV)
+    mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
+    g = torch.randn(2, 4, sc.H, sc.W, device=DEV)
+    import copy
+    for k in range(2):
+        sk = copy.copy(sc)
+        sk.extr = extrs[k]
+        ours, ref = _geometry(ms, sk), _geometry(ref_msplat, sk)
+        for name, a, b in zip(["uv", "depth", "conic", "radius", "tiles", "idx_sorted", "tile_range"], ours, ref):
+            assert torch.equal(a, b), f"view {k}: {name} differs from the reference"
+        # the batched sort of the fused path: same per-view order, ids offset by view * P', ranges by the batch
+        del ours, ref
+    A = mk()
+    imgs = ms.rasterization_sh_views(*A, sc.intr, extrs, sc.W, sc.H, 0.0, with_depth=True)
+    (imgs * g).sum().backward()
+
+    def run_ref():
+        B = mk()
+        for k in range(2):
+            img_r = steps_pipeline(ref_msplat, B, sc.intr, extrs[k], sc.W, sc.H, 0.0, True)
+            scale = max(1.0, float(img_r.detach().abs().max()))
+            err = float((imgs[k].detach() - img_r.detach()).abs().max())
+            assert err <= 1e-4 * scale, f"view {k}: image max abs error vs reference {err} (scale {scale})"
+            (img_r * g[k]).sum().backward()
+        return [t.grad for t in B]
+
+    ref, nf = spread(run_ref, n=1)
+    for n, a, b, f in zip(["xyz", "scale", "quat", "opacity", "shs"], A, ref, nf):
+        grad_close(a.grad, b, noise=f, what=f"config3 full size d{n}")
 
 
 def test_config3_full_size_properties(ms):
@@ -148,11 +229,17 @@ def test_config3_full_size_properties(ms):
     img2 = ms.rasterization_sh(*[p.detach() for p in P], sc.intr, sc.extr, sc.W, sc.H, 0.0, with_depth=True)
     assert torch.equal(img, img2)
     g1 = torch.randn(4, sc.H, sc.W, device=DEV)
-    (img * g1).sum().backward(retain_graph=True)
-    ga = [p.grad.clone() for p in P]
-    for p in P:
-        p.grad = None
-    (img * (2.0 * g1)).sum().backward()
-    for n, a, p in zip(["xyz", "scale", "quat", "opacity", "shs"], ga, P):
-        assert bool(torch.isfinite(p.grad).all())
-        grad_close(p.grad, 2.0 * a, rel=1e-3, eps=1e-4, what=f"linearity d{n}")
+
+    def backward(cot):
+        for p in P:
+            p.grad = None
+        (img * cot).sum().backward(retain_graph=True)
+        return [p.grad.clone() for p in P]
+
+    # three backward passes through the same graph: two with g1 (their difference is the run-to-run spread of
+    # our atomics-based backward blend = the noise floor), one with 2 g1 (linearity)
+    ga, gb = backward(g1), backward(g1)
+    g2 = backward(2.0 * g1)
+    for n, a, b, c in zip(["xyz", "scale", "quat", "opacity", "shs"], ga, gb, g2):
+        assert bool(torch.isfinite(c).all())
+        grad_close(c, 2.0 * a, noise=2.0 * float((a - b).abs().max()), what=f"config3 linearity d{n}")

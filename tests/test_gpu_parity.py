@@ -4,8 +4,13 @@ reference CUDA build in baseline/_ref when it travelled with the snapshot.
 
 Bars (BASELINE.json north_star):
   * tiles_touched, radius, gaussian_ids_sorted, tile_range: bit-exact vs the reference build;
-  * images: max abs 1e-4;  gradients: |d| <= 1e-3 |g| + 1e-4 max|g|  (the reference's own
-    gradients are atomics-order dependent).
+  * images: max abs 1e-4;
+  * gradients: |d| <= 1e-3 |g| + K_NOISE * noise_floor, where noise_floor is MEASURED in the test: the
+    run-to-run spread of the comparator itself (the reference's backward kernels accumulate with float
+    atomics, /root/reference/msplat/src/alpha_blending.cu:218,236-243, so its own gradients differ
+    between two runs on identical inputs -- SURVEY H7), never less than ULP_FLOOR * max|g| (what a
+    deterministic FP32 comparator still rounds at the tensor's scale).  tools/noise_floor.py reports the
+    spread per tensor at the benchmark sizes (profiles/r2_noise_floor.json).
 """
 import json
 import math
@@ -33,12 +38,53 @@ def cpu(t):
     return t.detach().cpu()
 
 
-def grad_close(a, b, rel=1e-3, eps=1e-4, what=""):
+REL = 1e-3            # the north star's relative gradient tolerance
+K_NOISE = 4.0         # multiples of the measured noise floor admitted on top of REL * |g|
+ULP_FLOOR = 2.0 ** -20  # floor of the noise floor, relative to max|g| (8 ulp at the tensor's scale)
+REPORT = []           # (what, max|g|, noise floor, max |d|, needed multiple of the floor) -> gpurun_out/
+
+
+def spread(fn, n=2):
+    """Run-to-run spread of a non-deterministic computation: fn() -> list of tensors, called n + 1 times;
+    returns (first result, [max |x_k - x_0| per tensor])."""
+    first = [t.detach().clone() for t in fn()]
+    nf = [0.0] * len(first)
+    for _ in range(n):
+        for k, t in enumerate(fn()):
+            nf[k] = max(nf[k], float((t.detach() - first[k]).abs().max())) if t.numel() else 0.0
+    return first, nf
+
+
+def grad_close(a, b, noise=0.0, what="", rel=REL, k=K_NOISE, min_frac=1.0):
+    """|a - b| <= rel |b| + k max(noise, ULP_FLOOR max|b|) for (at least a fraction min_frac of) the elements."""
     a, b = cpu(a).double(), cpu(b).double()
-    tol = rel * b.abs() + eps * max(float(b.abs().max()), 1e-30)
-    bad = (a - b).abs() > tol
-    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err " \
-                          f"{float((a - b).abs().max()):.3e} (scale {float(b.abs().max()):.3e})"
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    if b.numel() == 0:
+        return
+    scale = max(float(b.abs().max()), 1e-30)
+    floor = max(float(noise), ULP_FLOOR * scale)
+    d = (a - b).abs()
+    need = float(((d - rel * b.abs()) / floor).max())
+    REPORT.append({"what": what, "max_abs_g": scale, "noise_floor": float(noise), "max_abs_err": float(d.max()),
+                   "needed_k": need, "k": k, "rel": rel})
+    bad = d > rel * b.abs() + k * floor
+    frac_ok = 1.0 - float(bad.double().mean())
+    assert frac_ok >= min_frac, f"{what}: {int(bad.sum())}/{bad.numel()} outside {rel:g}|g| + {k:g} x {floor:.3e} " \
+                                f"(max err {float(d.max()):.3e}, scale {scale:.3e}, needs k = {need:.2f})"
+
+
+def compare_grads(run_ours, run_cmp, names, tag, n=2, noisy="cmp", min_frac=1.0):
+    """run_*() -> gradient tensors of a fresh forward + backward on identical inputs.  The side whose
+    backward accumulates with atomics (`noisy`: "cmp" = the comparator, "ours") is run n + 1 times to
+    measure its own run-to-run spread, which is the noise floor of the comparison."""
+    if noisy == "cmp":
+        cmp_, nf = spread(run_cmp, n)
+        ours = run_ours()
+    else:
+        ours, nf = spread(run_ours, n)
+        cmp_ = run_cmp()
+    for name, a, b, f in zip(names, ours, cmp_, nf):
+        grad_close(a, b, noise=f, what=f"{tag} {name}", min_frac=min_frac)
 
 
 def camera(W, H, kind="rot"):
@@ -90,10 +136,11 @@ def test_project_point_vs_oracle(ms, nearest, extent):
     uv_r, d_r = oracle.project_point(x64, i64, e64, W, H, nearest, extent)
     keep = (~culled)[:, None].double()  # use OUR culling set so both sides sum the same points
     ((uv_r * guv.double() * keep).sum() + (d_r * gd.double() * keep).sum()).backward()
-    if (culled != culled_o).sum() == 0:
-        grad_close(x.grad, x64.grad, what="dL_dxyz")
-        grad_close(i.grad, i64.grad, rel=2e-3, what="dL_dintr")
-        grad_close(e.grad, e64.grad, rel=2e-3, what="dL_dextr")
+    # unconditional: the float64 oracle's loss was restricted to OUR culling set above, so both sides
+    # differentiate the same sum even when a culling decision at a limit differs
+    grad_close(x.grad, x64.grad, what="project_point/oracle dL_dxyz")
+    grad_close(i.grad, i64.grad, what="project_point/oracle dL_dintr")
+    grad_close(e.grad, e64.grad, what="project_point/oracle dL_dextr")
 
 
 def test_project_point_vs_reference(ms, ref_msplat):
@@ -103,23 +150,25 @@ def test_project_point_vs_reference(ms, ref_msplat):
         intr, extr = camera(W, H, kind)
         if kind == "ident":
             xyz = xyz + torch.tensor([0.0, 0.0, 6.0])
-        x1, x2 = xyz.to(DEV).requires_grad_(), xyz.to(DEV).requires_grad_()
-        i1, i2 = intr.to(DEV).requires_grad_(), intr.to(DEV).requires_grad_()
-        e1, e2 = extr.to(DEV).requires_grad_(), extr.to(DEV).requires_grad_()
-        uv, d = ms.project_point(x1, i1, e1, W, H)
-        uv_r, d_r = ref_msplat.project_point(x2, i2, e2, W, H)
-        assert torch.equal(uv, uv_r) and torch.equal(d, d_r), "uv/depth must be bit-identical to the reference"
         g = torch.Generator().manual_seed(2)
         guv, gd = torch.randn(P, 2, generator=g).to(DEV), torch.randn(P, 1, generator=g).to(DEV)
-        ((uv * guv).sum() + (d * gd).sum()).backward()
-        ((uv_r * guv).sum() + (d_r * gd).sum()).backward()
-        grad_close(x1.grad, x2.grad, what="dL_dxyz vs ref")
-        grad_close(i1.grad, i2.grad, rel=2e-3, what="dL_dintr vs ref")
-        grad_close(e1.grad, e2.grad, rel=2e-3, what="dL_dextr vs ref")
+        out = {}
+
+        def run(api):
+            x, i, e = xyz.to(DEV).requires_grad_(), intr.to(DEV).requires_grad_(), extr.to(DEV).requires_grad_()
+            uv, d = api.project_point(x, i, e, W, H)
+            out[api] = (uv.detach(), d.detach())
+            ((uv * guv).sum() + (d * gd).sum()).backward()
+            return [x.grad, i.grad, e.grad]
+
+        compare_grads(lambda: run(ms), lambda: run(ref_msplat), ["dL_dxyz", "dL_dintr", "dL_dextr"],
+                      f"project_point/ref[{kind}]")
+        (uv, d), (uv_r, d_r) = out[ms], out[ref_msplat]
+        assert torch.equal(uv, uv_r) and torch.equal(d, d_r), "uv/depth must be bit-identical to the reference"
     # [4,4] extrinsics: only the first 12 floats are read
     e44 = torch.cat([extr, torch.tensor([[0.0, 0, 0, 1]])], 0).to(DEV)
     uv4, d4 = ms.project_point(xyz.to(DEV), intr.to(DEV), e44, W, H)
-    assert torch.equal(uv4, uv.detach()) and torch.equal(d4, d.detach())
+    assert torch.equal(uv4, uv) and torch.equal(d4, d)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,8 +188,8 @@ def test_compute_cov3d(ms, ref_msplat=None):
     (cov * g.to(DEV)).sum().backward()
     s64, q64 = scale.double().requires_grad_(), quat.double().requires_grad_()
     (oracle.compute_cov3d(s64, q64, vis) * g.double()).sum().backward()
-    grad_close(s.grad, s64.grad, what="dL_dscale")
-    grad_close(q.grad, q64.grad, what="dL_dquat")
+    grad_close(s.grad, s64.grad, what="cov3d/oracle dL_dscale")
+    grad_close(q.grad, q64.grad, what="cov3d/oracle dL_dquat")
     # default visible = all; [P,1] mask accepted
     cov_all = ms.compute_cov3d(scale.to(DEV), quat.to(DEV))
     torch.testing.assert_close(cpu(cov_all), oracle.compute_cov3d(scale, quat), rtol=1e-5, atol=1e-7)
@@ -159,8 +208,8 @@ def test_compute_cov3d_vs_reference(ms, ref_msplat):
     g = torch.randn(P, 6, device=DEV)
     (cov * g).sum().backward()
     (cov_r * g).sum().backward()
-    grad_close(s1.grad, s2.grad, what="dL_dscale vs ref")
-    grad_close(q1.grad, q2.grad, what="dL_dquat vs ref")
+    grad_close(s1.grad, s2.grad, what="cov3d/ref dL_dscale")  # no atomics on either side: noise floor = ULP floor
+    grad_close(q1.grad, q2.grad, what="cov3d/ref dL_dquat")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,11 +246,12 @@ def test_ewa_project_vs_oracle(ms):
     co, _, _ = oracle.ewa_project(x64, c64, i64, e64, uv.double(), W, H, vis)
     sel = (cpu(radius) > 0)[:, None].double()
     (co * g.double() * sel).sum().backward()
-    if not mism.any():
-        grad_close(x.grad, x64.grad, what="dL_dxyz")
-        grad_close(c.grad, c64.grad, what="dL_dcov3d")
-        grad_close(i.grad[:2], i64.grad[:2], rel=3e-3, what="dL_dintr")
-        grad_close(e.grad, e64.grad, rel=3e-3, what="dL_dextr")
+    # unconditional: the oracle's loss is restricted to OUR radius > 0 set (sel), so a radius that flips at
+    # ceil() does not change which Gaussians are differentiated
+    grad_close(x.grad, x64.grad, what="ewa/oracle dL_dxyz")
+    grad_close(c.grad, c64.grad, what="ewa/oracle dL_dcov3d")
+    grad_close(i.grad[:2], i64.grad[:2], what="ewa/oracle dL_dintr")
+    grad_close(e.grad, e64.grad, what="ewa/oracle dL_dextr")
 
 
 def test_ewa_project_vs_reference(ms, ref_msplat):
@@ -215,22 +265,23 @@ def test_ewa_project_vs_reference(ms, ref_msplat):
         uv, depth = ref_msplat.project_point(xd, id_, ed, W, H)
         vis = (depth != 0).squeeze(-1)
         cov = ref_msplat.compute_cov3d(scale.to(DEV), quat.to(DEV), vis)
-        x1, x2 = xd.clone().requires_grad_(), xd.clone().requires_grad_()
-        c1, c2 = cov.clone().requires_grad_(), cov.clone().requires_grad_()
-        i1, i2 = id_.clone().requires_grad_(), id_.clone().requires_grad_()
-        e1, e2 = ed.clone().requires_grad_(), ed.clone().requires_grad_()
-        conic, radius, tiles = ms.ewa_project(x1, c1, i1, e1, uv, W, H, vis)
-        conic_r, radius_r, tiles_r = ref_msplat.ewa_project(x2, c2, i2, e2, uv, W, H, vis)
+        g = torch.randn(P, 3, device=DEV)
+        out = {}
+
+        def run(api):
+            L = [t.clone().requires_grad_() for t in (xd, cov, id_, ed)]
+            conic, radius, tiles = api.ewa_project(L[0], L[1], L[2], L[3], uv, W, H, vis)
+            out[api] = (conic.detach(), radius, tiles)
+            (conic * g).sum().backward()
+            return [t.grad for t in L]
+
+        # the reference's camera gradients are ~25 same-address atomics per Gaussian (ewa_project.cu:299-345)
+        compare_grads(lambda: run(ms), lambda: run(ref_msplat), ["dL_dxyz", "dL_dcov3d", "dL_dintr", "dL_dextr"],
+                      f"ewa/ref[{W}x{H}]")
+        (conic, radius, tiles), (conic_r, radius_r, tiles_r) = out[ms], out[ref_msplat]
         assert torch.equal(radius, radius_r), f"{int((radius != radius_r).sum())} radius mismatches"
         assert torch.equal(tiles, tiles_r), f"{int((tiles != tiles_r).sum())} tiles_touched mismatches"
         assert torch.equal(conic, conic_r), "conic not bit-identical"
-        g = torch.randn(P, 3, device=DEV)
-        (conic * g).sum().backward()
-        (conic_r * g).sum().backward()
-        grad_close(x1.grad, x2.grad, what="dL_dxyz vs ref")
-        grad_close(c1.grad, c2.grad, what="dL_dcov3d vs ref")
-        grad_close(i1.grad, i2.grad, rel=3e-3, what="dL_dintr vs ref")
-        grad_close(e1.grad, e2.grad, rel=3e-3, what="dL_dextr vs ref")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -401,6 +452,53 @@ def test_sort_vs_reference(ms, ref_msplat):
         assert torch.equal(ids, ids_r), f"{int((ids != ids_r).sum())}/{ids.numel()} sorted ids differ from the reference"
 
 
+def test_sort_views_equals_per_view_sorts(ms, ref_msplat):
+    """One batched sort of B views (view | tile | depth keys over views * P virtual Gaussians) yields, view by
+    view, exactly the reference's idx_sorted / tile_range (ids offset by view * P, positions by the lists of
+    the views before)."""
+    B, P, W, H = 3, 60000, 800, 608
+    per = [_sort_inputs(P, W, H, 30 + b, 1.0 + b, tie=(b == 1)) for b in range(B)]
+    uv = torch.stack([p[0] for p in per]).to(DEV)
+    depth = torch.stack([p[1].reshape(-1) for p in per]).to(DEV)
+    radius = torch.stack([p[2] for p in per]).to(DEV)
+    tiles = torch.stack([p[3] for p in per]).to(DEV)
+    ids, tr = ms.sort_gaussian_views(uv, depth, W, H, radius, tiles)
+    T = tr.shape[1]
+    assert tr.shape == (B, T, 2) and ids.numel() == int(tiles.sum())
+    off = 0
+    for b in range(B):
+        ids_r, tr_r = ref_msplat.sort_gaussian(uv[b], depth[b][:, None], W, H, radius[b], tiles[b])
+        Mb = ids_r.numel()
+        assert torch.equal(ids[off:off + Mb] - b * P, ids_r), f"view {b}: sorted ids differ from the reference"
+        nonempty = (tr_r[:, 1] > tr_r[:, 0])[:, None]
+        assert torch.equal(torch.where(nonempty, tr[b] - off, tr[b]), tr_r), f"view {b}: tile_range differs"
+        off += Mb
+
+
+def test_sort_more_than_2_30_keys(ms):
+    """M = 1.2 x 2^30 tile intersections (the reference admits M < 2^31: int32 cumsum,
+    msplat/sort_gaussian.py:42).  Every Gaussian covers the whole 512 x 512 image (1024 tiles), so the
+    expected result is known in closed form: each tile's list is all Gaussians in (depth, index) order."""
+    P, W, H = 1_258_292, 512, 512
+    T = 1024
+    g = torch.Generator().manual_seed(5)
+    uv = (torch.rand(P, 2, generator=g) * 512).to(DEV)
+    depth = (torch.rand(P, 1, generator=g) * 0.5 + 0.5).to(DEV)   # 2^22 distinct values: plenty of ties
+    depth = torch.round(depth * 4096) / 4096
+    radius = torch.full((P,), 2000, dtype=torch.int32, device=DEV)
+    tiles = torch.full((P,), T, dtype=torch.int32, device=DEV)
+    M = P * T
+    assert 2 ** 30 < M < 2 ** 31
+    ids, tr = ms.sort_gaussian(uv, depth, W, H, radius, tiles)
+    assert ids.numel() == M
+    want_tr = torch.stack([torch.arange(T, device=DEV) * P, (torch.arange(T, device=DEV) + 1) * P], dim=1).to(torch.int32)
+    assert torch.equal(tr, want_tr)
+    order = torch.sort(depth.reshape(-1), stable=True).indices.to(torch.int32)  # ties keep index order
+    for t in (0, 1, 511, 1023):
+        assert torch.equal(ids[t * P:(t + 1) * P], order), f"tile {t}: list is not the stable depth order"
+    assert int((ids.view(T, P) != order[None]).sum()) == 0
+
+
 def test_sort_properties_large(ms):
     """Size-independent properties at a BASELINE-scale size: every tile's list is depth-sorted,
     the ranges tile [0, M) exactly, and the multiset of ids matches tiles_touched."""
@@ -451,24 +549,34 @@ def _blend_inputs(P, W, H, C, seed, mul=1.0):
 def test_alpha_blending_vs_oracle(ms, C, bg):
     P, W, H = 6000, 200, 120
     uv, conic, opacity, feat, ids, tr = _blend_inputs(P, W, H, C, 20 + C, mul=1.5)
-    u, c = uv.to(DEV).requires_grad_(), conic.to(DEV).requires_grad_()
-    o, f = opacity.to(DEV).requires_grad_(), feat.to(DEV).requires_grad_()
-    img = ms.alpha_blending(u, c, o, f, ids.to(DEV), tr.to(DEV), bg, W, H)
-    assert img.shape == (C, H, W)
-    u2, c2 = uv.clone().requires_grad_(), conic.clone().requires_grad_()
-    o2, f2 = opacity.clone().requires_grad_(), feat.clone().requires_grad_()
-    img_o = oracle.alpha_blending(u2, c2, o2, f2, ids, tr, bg, W, H)
-    err = (cpu(img) - img_o.detach()).abs()
-    # expf (oracle) vs ex2.approx (device): a pair exactly at a threshold may flip for a pixel or two
-    assert float(err.max()) <= 1e-4 or int((err.amax(0) > 1e-4).sum()) <= 3, f"max abs image error {float(err.max())}"
     g = torch.randn(C, H, W, generator=torch.Generator().manual_seed(7))
-    (img * g.to(DEV)).sum().backward()
-    (img_o * g).sum().backward()
-    if float(err.max()) <= 1e-4:
-        grad_close(u.grad, u2.grad, rel=2e-3, eps=2e-4, what="dL_duv")
-        grad_close(c.grad, c2.grad, rel=2e-3, eps=2e-4, what="dL_dconic")
-        grad_close(o.grad, o2.grad, rel=2e-3, eps=2e-4, what="dL_dopacity")
-        grad_close(f.grad, f2.grad, rel=2e-3, eps=2e-4, what="dL_dfeature")
+    out = {}
+
+    def run_ours():
+        L = [t.to(DEV).requires_grad_() for t in (uv, conic, opacity, feat)]
+        img = ms.alpha_blending(*L, ids.to(DEV), tr.to(DEV), bg, W, H)
+        out["img"] = img.detach()
+        (img * g.to(DEV)).sum().backward()
+        return [t.grad for t in L]
+
+    def run_oracle():
+        L = [t.clone().requires_grad_() for t in (uv, conic, opacity, feat)]
+        img_o = oracle.alpha_blending(*L, ids, tr, bg, W, H)
+        out["img_o"] = img_o.detach()
+        (img_o * g).sum().backward()
+        return [t.grad for t in L]
+
+    ours, nf = spread(run_ours)       # our backward accumulates with red.global: its spread is the noise floor
+    ref = run_oracle()
+    assert out["img"].shape == (C, H, W)
+    err = (cpu(out["img"]) - out["img_o"]).abs()
+    # expf (oracle) vs ex2.approx (device): a pair exactly at a threshold may flip for a pixel or two
+    flips = int((err.amax(0) > 1e-4).sum())
+    assert flips <= 3, f"max abs image error {float(err.max())} on {flips} pixels"
+    # always compared: a flipped pixel changes the gradients of the few Gaussians it blends, so with flips
+    # 99.9 % of the elements must agree, without flips all of them
+    for name, a, b, f in zip(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature"), ours, ref, nf):
+        grad_close(a, b, noise=f, what=f"blend/oracle[C={C}] {name}", min_frac=1.0 if flips == 0 else 0.999)
 
 
 def test_alpha_blending_reference_test_shape(ms, golden):
@@ -484,10 +592,13 @@ def test_alpha_blending_reference_test_shape(ms, golden):
     img = ms.alpha_blending(u, c, o, f, ids, tr, bg, W, H)
     torch.testing.assert_close(cpu(img), torch.from_numpy(g["image"]), rtol=1e-4, atol=1e-4)
     img.sum().backward()
-    grad_close(u.grad, torch.from_numpy(g["duv"]), rel=2e-3, eps=5e-4, what="dL_duv")
-    grad_close(c.grad, torch.from_numpy(g["dconic"]), rel=2e-3, eps=5e-4, what="dL_dconic")
-    grad_close(o.grad, torch.from_numpy(g["dopacity"]), rel=2e-3, eps=5e-4, what="dL_dopacity")
-    grad_close(f.grad, torch.from_numpy(g["dfeature"]), rel=2e-3, eps=5e-4, what="dL_dfeature")
+    # golden gradients come from float32 autograd of the reference's loop restatement (CPU): their own
+    # rounding is part of the floor, so the fixture's tolerance (test/test_alpha_blending.py:196-199: atol 1e-4)
+    # is stated as a noise floor
+    grad_close(u.grad, torch.from_numpy(g["duv"]), noise=1e-4, k=1.0, what="blend/golden dL_duv")
+    grad_close(c.grad, torch.from_numpy(g["dconic"]), noise=1e-4, k=1.0, what="blend/golden dL_dconic")
+    grad_close(o.grad, torch.from_numpy(g["dopacity"]), noise=1e-4, k=1.0, what="blend/golden dL_dopacity")
+    grad_close(f.grad, torch.from_numpy(g["dfeature"]), noise=1e-4, k=1.0, what="blend/golden dL_dfeature")
 
 
 def test_alpha_blending_vs_reference(ms, ref_msplat):
@@ -496,18 +607,22 @@ def test_alpha_blending_vs_reference(ms, ref_msplat):
                                   (20000, 400, 300, 33, 0.5, 2.0), (20000, 333, 217, 12, 0.0, 2.0)]:
         uv, conic, opacity, feat, ids, tr = _blend_inputs(P, W, H, C, 40 + C, mul)
         a = [t.to(DEV) for t in (uv, conic, opacity, feat, ids, tr)]
-        l1 = [t.clone().requires_grad_() for t in a[:4]]
-        l2 = [t.clone().requires_grad_() for t in a[:4]]
-        img = ms.alpha_blending(l1[0], l1[1], l1[2], l1[3], a[4], a[5], bg, W, H)
-        img_r = ref_msplat.alpha_blending(l2[0], l2[1], l2[2], l2[3], a[4], a[5], bg, W, H)
+        g = torch.randn(C, H, W, device=DEV)
+        out = {}
+
+        def run(api):
+            L = [t.clone().requires_grad_() for t in a[:4]]
+            img = api.alpha_blending(L[0], L[1], L[2], L[3], a[4], a[5], bg, W, H)
+            out[api] = img.detach()
+            (img * g).sum().backward()
+            return [t.grad for t in L]
+
+        compare_grads(lambda: run(ms), lambda: run(ref_msplat), ("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature"),
+                      f"blend/ref[P={P},C={C}]")
+        img, img_r = out[ms], out[ref_msplat]
         err = float((img - img_r).abs().max())
         report[f"P{P}_C{C}"] = {"max_abs": err, "bit_exact": bool(torch.equal(img, img_r))}
         assert err <= 1e-4, f"image max abs error vs reference {err}"
-        g = torch.randn(C, H, W, device=DEV)
-        (img * g).sum().backward()
-        (img_r * g).sum().backward()
-        for k, name in enumerate(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature")):
-            grad_close(l1[k].grad, l2[k].grad, rel=2e-3, eps=2e-4, what=name + " vs ref")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "blend_vs_ref.json"), "w"), indent=1)
 
@@ -530,18 +645,26 @@ def test_rasterization_fused_equals_steps_and_oracle(ms):
     (img_f * g.to(DEV)).sum().backward()
     (img_s * g.to(DEV)).sum().backward()
     names = ["xyz", "scale", "quat", "opacity", "feature", "intr", "extr"]
-    for n, a, b in zip(names, A, B):
-        grad_close(a.grad, b.grad, rel=2e-3, eps=2e-4, what=f"fused vs steps d{n}")
-    grad_close(ndc_a.grad, ndc_b.grad, rel=2e-3, eps=2e-4, what="dL_dndc")
+
+    def run_steps():
+        Bk = leaves()
+        nd = torch.zeros(P, 2, device=DEV, requires_grad=True)
+        (ms.rasterization(*Bk, W, H, 0.3, nd, fused=False) * g.to(DEV)).sum().backward()
+        return [t.grad for t in Bk] + [nd.grad]
+
+    _, nf = spread(run_steps)  # both sides share the atomics-based backward blend: its spread is the floor
+    for n, a, b, f in zip(names, A, B, nf):
+        grad_close(a.grad, b.grad, noise=f, what=f"rasterization fused/steps d{n}")
+    grad_close(ndc_a.grad, ndc_b.grad, noise=nf[-1], what="rasterization fused/steps dL_dndc")
     # oracle end to end (float32 torch on CPU + C blend)
     O = [t.clone().requires_grad_() for t in (xyz, scale, quat, opacity, feat, intr, extr)]
     img_o = oracle.rasterization(*O, W, H, 0.3)
     err = (cpu(img_f) - img_o.detach()).abs()
-    assert float(err.max()) <= 1e-4 or int((err.amax(0) > 1e-4).sum()) <= 5, f"image err {float(err.max())}"
+    flips = int((err.amax(0) > 1e-4).sum())
+    assert flips <= 5, f"image err {float(err.max())} on {flips} pixels"
     (img_o * g).sum().backward()
-    if float(err.max()) <= 1e-4:
-        for n, a, o in zip(names[:5], A[:5], O[:5]):
-            grad_close(a.grad, o.grad, rel=5e-3, eps=5e-4, what=f"vs oracle d{n}")
+    for n, a, o, f in zip(names[:5], A[:5], O[:5], nf):  # always compared (see test_alpha_blending_vs_oracle)
+        grad_close(a.grad, o.grad, noise=f, what=f"rasterization/oracle d{n}", min_frac=1.0 if flips == 0 else 0.999)
 
 
 def test_rasterization_vs_reference(ms, ref_msplat):
@@ -550,16 +673,21 @@ def test_rasterization_vs_reference(ms, ref_msplat):
     C = 3
     feat = torch.rand(sc.xyz.shape[0], C, device=DEV)
     mk = lambda: [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, feat, sc.intr, sc.extr)]
-    A, B = mk(), mk()
-    img = ms.rasterization(*A, sc.W, sc.H, 0.0)
-    img_r = ref_msplat.rasterization(*B, sc.W, sc.H, 0.0)
+    g = torch.randn(C, sc.H, sc.W, device=DEV)
+    out = {}
+
+    def run(api):
+        L = mk()
+        img = api.rasterization(*L, sc.W, sc.H, 0.0)
+        out[api] = img.detach()
+        (img * g).sum().backward()
+        return [t.grad for t in L]
+
+    compare_grads(lambda: run(ms), lambda: run(ref_msplat),
+                  ["dxyz", "dscale", "dquat", "dopacity", "dfeature", "dintr", "dextr"], "rasterization/ref")
+    img, img_r = out[ms], out[ref_msplat]
     err = float((img - img_r).abs().max())
     assert err <= 1e-4, f"image max abs error vs reference {err}"
-    g = torch.randn(C, sc.H, sc.W, device=DEV)
-    (img * g).sum().backward()
-    (img_r * g).sum().backward()
-    for n, a, b in zip(["xyz", "scale", "quat", "opacity", "feature", "intr", "extr"], A, B):
-        grad_close(a.grad, b.grad, rel=5e-3, eps=5e-4, what=f"d{n} vs ref")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"max_abs": err, "bit_exact": bool(torch.equal(img, img_r))},
               open(os.path.join(ROOT, "gpurun_out", "raster_vs_ref.json"), "w"))
