@@ -16,7 +16,12 @@ coefficients summed over the views.  Two ways to write that step against the pub
                the view batch (fused per-Gaussian kernels, gradients accumulated in-kernel);
                default for --impl ours, which also reports the steps-API number as `steps_api`
 With N > 1 every rank renders its own `views` cameras (weak scaling) and the per-Gaussian
-gradients are sum-all-reduced once per step (NCCL).  value = N * views / step_time.
+gradients are summed over the ranks once per step (NCCL; only the rows some rank touched travel).
+value = N * views / step_time.
+
+--config 5        BASELINE configs[4] instead of configs[2]: 6M Gaussians, 3840x2160, a batch of 64
+                  cameras STRONG-scaled over the N ranks (64 / N views per rank), one gradient exchange
+                  per step; value = 64 / step_time, "scaling": "strong".
 
 --impl ours       msplat_b200 (default)
 --impl reference  the UNMODIFIED reference CUDA build from baseline/_ref through its own public
@@ -44,6 +49,8 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "fwd+bwd renders/s @3M Gaussians 1080p SH3"
 P_FULL, W_FULL, H_FULL, SH_DEG, SIGMA = 3_000_000, 1920, 1080, 3, 2.0
+METRIC5 = "fwd+bwd renders/s, view-batch training step @6M Gaussians 4K, 64 cameras"
+P5, W5, H5, SIGMA5, VIEWS5 = 6_000_000, 3840, 2160, 3.0, 64
 
 
 # ------------------------------------------------------------------------------------------------
@@ -157,29 +164,31 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
-# algorithmic HBM bytes per unit of each C-ABI call at SH3 RGB + depth (DESIGN.md "Kernels")
-def algorithmic_bytes(name, P, M, Cs, D, C, nvis=None, views=1, nlive=None):
-    nvis = P if nvis is None else nvis
-    nlive = nvis if nlive is None else nlive  # Gaussians that received a colour gradient (<= nvis)
+# algorithmic HBM bytes per STEP (V views of one rank) of each C-ABI entry point at SH `Cs x D` colours and
+# `cpad` blend channels (DESIGN.md "Kernels"); the stage table divides them by the measured time per step,
+# whatever number of launches (view chunks, Gaussian slabs) the step was split into
+def algorithmic_bytes(name, P, M, Cs, D, cpad, V, nvis_any=None, nlive_any=None):
+    nvis_any = P if nvis_any is None else nvis_any      # Gaussians touching a tile in at least one view
+    nlive_any = nvis_any if nlive_any is None else nlive_any  # ... that receive a colour gradient in at least one view
     sh = 4 * Cs * D
-    # backward: the first view of a step writes every output, the others accumulate (read + write)
-    acc = (views - 1) / max(views, 1)
+    per_view_out = 32 + 4 * cpad + 8 + 4 + 4 + 4        # rec, featp, uv, depth, radius, tiles
     T = {
-        "render_preprocess_forward": P * (44 + 32 + 16 + 8 + 12) + nvis * sh,
-        # inputs + packed grads + tiles; SH rows of the live Gaussians; 44 B of geometry grads (RMW when
-        # accumulating); dL_dshs: every row written by the first view, live rows read + written by the others
-        "render_preprocess_backward": P * (40 + 32 + 16 + 4) + nlive * sh + P * 44 * (1 + acc)
-                                      + (1 - acc) * P * sh + acc * nlive * 2 * sh,
-        "project_point_forward": P * (12 + 12),
-        "project_point_backward": P * (12 + 4 + 12 + 12),
-        "compute_cov3d_forward": P * (12 + 16 + 1 + 24),
-        "compute_cov3d_backward": P * (12 + 16 + 1 + 24 + 28),
-        "ewa_project_forward": P * (12 + 24 + 8 + 1 + 12 + 8),
-        "ewa_project_backward": P * (12 + 24 + 4 + 12 + 12 + 24),
-        "compute_sh_forward": P * (4 * Cs * D + 12 + 1 + 4 * Cs),
-        "compute_sh_backward": P * (2 * 4 * Cs * D + 12 + 1 + 4 * Cs + 12),
-        "sort_scan": P * (4 + 4 + 4),
-        "sort_gaussian": P * 20 + M * (12 + 24 * 6 + 8),
+        # parameters + SH rows once, per-view packed records out
+        "render_preprocess_forward": P * 44 + nvis_any * sh + V * P * per_view_out,
+        # parameters once, per view tiles + packed gradients in, SH rows of the live Gaussians once,
+        # geometry gradients and dL_dshs written once
+        "render_preprocess_backward": P * 40 + V * P * (4 + 32 + 4 * cpad) + nlive_any * sh + P * 44 + P * sh,
+        "project_point_forward": V * P * (12 + 12),
+        "project_point_backward": V * P * (12 + 4 + 12 + 12),
+        "compute_cov3d_forward": V * P * (12 + 16 + 1 + 24),
+        "compute_cov3d_backward": V * P * (12 + 16 + 1 + 24 + 28),
+        "ewa_project_forward": V * P * (12 + 24 + 8 + 1 + 12 + 8),
+        "ewa_project_backward": V * P * (12 + 24 + 4 + 12 + 12 + 24),
+        "compute_sh_forward": V * P * (4 * Cs * D + 12 + 1 + 4 * Cs),
+        "compute_sh_backward": V * P * (2 * 4 * Cs * D + 12 + 1 + 4 * Cs + 12),
+        "sort_scan": V * P * (4 + 4 + 4),
+        # 20 B per Gaussian and view, 12 + 8 + 24 p + 8 B per key with p = 6 digit passes
+        "sort_gaussian": V * P * 20 + M * (12 + 24 * 6 + 8),
     }
     return T.get(name)
 
@@ -206,10 +215,15 @@ def run_gpu(args, api, impl):
 
     ours = impl == "ours"
     P, W, H = args.gaussians, args.width, args.height
-    scene = frustum_scene(P, W, H, SIGMA, seed=0, sh_degree=SH_DEG).to(dev)
+    cfg5 = args.config == 5
+    if cfg5:
+        if VIEWS5 % world:
+            raise SystemExit(f"--config 5 shards {VIEWS5} cameras: N must divide it")
+        args.views = VIEWS5 // world  # strong scaling: the 64-camera batch is split over the ranks
+    scene = frustum_scene(P, W, H, args.sigma, seed=0, sh_degree=SH_DEG).to(dev)
     params = [t.clone().requires_grad_() for t in (scene.xyz, scene.scale, scene.quat, scene.opacity, scene.shs)]
     V = args.views
-    cams_host = make_cameras(scene, V * world, "cpu")[rank * V:(rank + 1) * V]
+    cams_host = make_cameras(scene, VIEWS5 if cfg5 else V * world, "cpu")[rank * V:(rank + 1) * V]
     C = 4
     G_host = torch.randn(C, H, W, generator=torch.Generator().manual_seed(1)).pin_memory()
     G = G_host.to(dev)
@@ -231,13 +245,15 @@ def run_gpu(args, api, impl):
         flat.all_reduce()
         return total
 
+    dp_stats = {} if world > 1 else None
+
     def step_fused(intrs, extrs, cents, G_):
         """one autograd Function over the view batch; gradients come back already summed"""
         for p_ in params:
             p_.grad = None
         images = api.rasterization_sh_views(*params, intrs, extrs, W, H, 0.0, with_depth=True,
                                             grad_sync=(world > 1),  # grads come back summed over the ranks
-                                            grad_chunks=args.grad_chunks)
+                                            grad_chunks=args.grad_chunks, view_chunk=args.view_chunk, stats=dp_stats)
         loss = (images * resolve(G_)).sum()
         loss.backward()
         return loss.detach()
@@ -268,17 +284,16 @@ def run_gpu(args, api, impl):
             # per-C-ABI-call durations: same steps again, serialised on one stream (no sort/blend overlap),
             # each call bracketed by CUDA events on its launching stream
             from msplat_b200 import render as _render
-            prev, _render.OVERLAP = _render.OVERLAP, False
-            step(*dev_in)
-            barrier_sync(world)
-            _lib.TIMING = []
-            e0.record()
-            for _ in range(args.steps):
+            with _render.serialised():
                 step(*dev_in)
-            e1.record()
-            barrier_sync(world)
-            timing, _lib.TIMING = _lib.TIMING, None
-            _render.OVERLAP = prev
+                barrier_sync(world)
+                _lib.TIMING = []
+                e0.record()
+                for _ in range(args.steps):
+                    step(*dev_in)
+                e1.record()
+                barrier_sync(world)
+                timing, _lib.TIMING = _lib.TIMING, None
             serial_ms = e0.elapsed_time(e1) / args.steps
             # the same per-call events with the two-stream schedule on: how long each call takes while it
             # shares the SMs with the other stream's kernels
@@ -328,17 +343,25 @@ def run_gpu(args, api, impl):
                                                                                  stages=True)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
-    api_note = ("msplat_b200.rasterization_sh_views (fused view-batch Function)" if fused else
+    api_note = ("msplat_b200.rasterization_sh_views (fused view-batch Function: one preprocess / sort / blend launch "
+                "per view batch)" if fused else
                 "steps API: project_point/compute_sh/compute_cov3d/ewa_project/sort_gaussian/alpha_blending per view")
+    sync_note = ""
+    if world > 1:
+        sync_note = (", per-Gaussian grads summed over the ranks once per step (NCCL all-reduce of the rows some rank "
+                     "touched)" if fused else ", one NCCL sum all-reduce of the flat grads per step")
     out = {
-        "metric": METRIC, "value": value, "unit": "renders/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"S-frustum(P={P}, {W}x{H}, sigma_med={SIGMA}, seed=0), SH degree {SH_DEG}, "
-                               f"RGB+depth (C=4), fwd+bwd, {V} views per rank per step, grads to xyz/scale/rot/"
-                               f"opacity/shs" + (", one NCCL sum all-reduce of the grads per step" if world > 1 else ""),
+        "metric": METRIC5 if cfg5 else METRIC, "value": value, "unit": "renders/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if cfg5 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"S-frustum(P={P}, {W}x{H}, sigma_med={args.sigma}, seed=0), SH degree {SH_DEG}, "
+                               f"RGB+depth (C=4), fwd+bwd, {V} views per rank per step"
+                               + (f" ({VIEWS5} cameras over {world} ranks)" if cfg5 else "")
+                               + ", grads to xyz/scale/rot/opacity/shs" + sync_note,
+                   "baseline_config": 5 if cfg5 else 3,
                    "gaussians": P, "width": W, "height": H, "sh_degree": SH_DEG, "channels": C,
                    "views_per_rank_per_step": V, "parallelism": f"view-dp{world}", "api": api_note,
+                   "view_chunk": args.view_chunk, "grad_chunks": args.grad_chunks,
                    "cache": "inputs (~0.7 GB of parameters per render) exceed the 126 MB L2; no explicit flush"},
         "impl": impl, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "renders/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -348,8 +371,13 @@ def run_gpu(args, api, impl):
         timing, serial_ms, overlapped = timing
         out["serial_ms_per_step"] = serial_ms  # same step with the two-stream overlap switched off (stage timings)
         out["stage_ms_two_stream"] = overlapped  # per-call durations while overlapping with the other stream
-        out.update(stage_report(timing, args, api, params, cams_host[0], G, clocks, V))
-        if fused and not args.no_steps_api:
+        out.update(stage_report(timing, args, api, params, cams_host, G, clocks, V, world))
+        if dp_stats:
+            sent, dense = dp_stats.get("allreduce_floats"), dp_stats.get("allreduce_dense_floats")
+            if sent and dense:
+                out["grad_exchange"] = {"bytes_per_step": 4 * sent, "dense_bytes": 4 * dense,
+                                        "fraction_of_dense": round(sent / dense, 4)}
+        if fused and not args.no_steps_api and not cfg5:
             s_ms, s_val, s_e2e, _, _, _ = measure(step_steps)
             out["steps_api"] = {"value": s_val, "e2e": s_e2e, "ms_per_step": s_ms, "unit": "renders/s",
                                 "note": "same workload written against the reference-style steps API of msplat_b200"}
@@ -359,106 +387,147 @@ def run_gpu(args, api, impl):
                                "sample": "full workload on the GPU through the unmodified reference build "
                                          "(baseline/_ref); no CPU implementation exists in the reference"}
     if rank == 0:
-        if ours and world == 1 and not args.no_cpu_baseline:
+        if ours and world == 1 and not args.no_cpu_baseline and not cfg5:
             out["cpu_baseline"] = cpu_baseline(args)
+            if not args.no_other_configs:
+                out["other_configs"] = other_configs(api, dev)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def stage_report(timing, args, api, params, cam, G, clocks, views):
-    """Per-C-ABI-call durations (CUDA events recorded on the launching stream inside the timed
-    region) -> roofline of the dominant call + a per-stage table."""
+def batch_counts(api, params, cams, W, H, C, G):
+    """Work counters of one step of this rank (all its views), from the steps API of our library:
+    M (keys), traversed pairs = sum(ncontrib), blended pairs (entries passing the power / alpha
+    tests before termination), Gaussians touching a tile / receiving a colour gradient in at least one view."""
     from msplat_b200 import _lib
+    from msplat_b200._lib import ptr
+    from msplat_b200.alpha_blending import _blend_backward, _blend_forward
+    L = _lib.lib()
+    P = params[0].shape[0]
+    Cs = params[4].shape[1]
+    M = pairs = blended = 0
+    vis_any = torch.zeros(P, dtype=torch.bool, device=params[0].device)
+    live_any = torch.zeros_like(vis_any)
+    with torch.no_grad():
+        xyz, scale, quat, opacity, shs = [p.detach() for p in params]
+        feat = torch.rand(P, C, device=xyz.device)
+        for cam in cams:
+            intr, extr = cam[0].to(xyz.device), cam[1].to(xyz.device)
+            uv, depth = api.project_point(xyz, intr, extr, W, H)
+            vis = depth != 0
+            cov = api.compute_cov3d(scale, quat, vis)
+            conic, radius, tiles = api.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+            ids, tr = api.sort_gaussian(uv, depth, W, H, radius, tiles)
+            _, final_T, ncontrib, packed = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
+            pairs += int(ncontrib.sum())
+            M += int(ids.numel())
+            vis_any |= tiles > 0
+            cnt = torch.empty((H, W), dtype=torch.int32, device=xyz.device)
+            _lib.call("blend_count", 1, L.msb_blend_packed_count, xyz.device, ptr(packed), ptr(ids), ptr(tr), W, H, 1,
+                      ptr(cnt))
+            blended += int(cnt.sum())
+            dfeat = _blend_backward(feat, ids, tr, 0.0, W, H, final_T, ncontrib, G[:C].contiguous(), packed)[3]
+            live_any |= (dfeat[:, :Cs] != 0).any(dim=1)
+            del dfeat, packed, ids, cnt
+    return {"keys": M, "pairs": pairs, "blended_pairs": blended, "nvis_any": int(vis_any.sum()),
+            "nlive_any": int(live_any.sum())}
+
+
+def stage_report(timing, args, api, params, cams, G, clocks, views, world):
+    """Per-C-ABI-call durations (CUDA events recorded on the launching stream inside the timed region, schedule
+    serialised) summed PER STEP of this rank -> roofline of the dominant stage + a per-stage table.  All rates are
+    per-step work / per-step time, so they do not depend on how many launches (view chunks, Gaussian slabs) a step
+    was split into."""
     P, W, H = args.gaussians, args.width, args.height
     Cs, D, C = 3, (SH_DEG + 1) ** 2, 4
+    cpad = 4
     agg = {}
     for name, a, b in timing:
         d = agg.setdefault(name, [0.0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += 1
-    # pairs = sum(ncontrib), M and the number of Gaussians touching a tile, for one representative view
-    with torch.no_grad():
-        xyz, scale, quat, opacity, shs = [p.detach() for p in params]
-        intr, extr = cam[0].to(xyz.device), cam[1].to(xyz.device)
-        uv, depth = api.project_point(xyz, intr, extr, W, H)
-        vis = depth != 0
-        cov = api.compute_cov3d(scale, quat, vis)
-        conic, radius, tiles = api.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
-        ids, tr = api.sort_gaussian(uv, depth, W, H, radius, tiles)
-        from msplat_b200.alpha_blending import _blend_forward
-        feat = torch.rand(P, C, device=xyz.device)
-        _, final_T, ncontrib, packed = _blend_forward(uv, conic, opacity.reshape(-1, 1), feat, ids, tr, 0.0, W, H)
-        pairs = int(ncontrib.sum())
-        M = int(ids.numel())
-        nvis = int((tiles > 0).sum())
-        # Gaussians that receive a colour gradient (blend at least one pixel): the only SH rows the backward touches
-        from msplat_b200.alpha_blending import _blend_backward
-        dfeat = _blend_backward(feat, ids, tr, 0.0, W, H, final_T, ncontrib, G[:C].contiguous(), packed)[3]
-        nlive = int((dfeat[:, :Cs] != 0).any(dim=1).sum())
-        del dfeat, packed
+    cnt = batch_counts(api, params, cams, W, H, C, G)
+    pairs, blended, M = cnt["pairs"], cnt["blended_pairs"], cnt["keys"]
     hbm, sm_max, src = measured_peaks()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     f_hz = (clocks["sm_mhz"] if clocks else sm_max) * 1e6
     total_ms = sum(v[0] for v in agg.values())
     is_blend = lambda n: n.startswith("alpha_blending") or n.startswith("blend_")
-    stages = {}
-    for name, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        ms = tot / n
-        st = {"ms": round(ms, 4), "share": round(tot / total_ms, 4), "calls": n}
-        ab = algorithmic_bytes(name, P, M, Cs, D, C, nvis, views, nlive)
-        if ab is not None:
-            st["GBps"] = round(ab / (ms * 1e-3) / 1e9, 1)
-            st["hbm_frac"] = round(st["GBps"] / hbm, 3)
-            st["algorithmic_MB"] = round(ab / 1e6, 1)
-        if is_blend(name):
-            st["Gpairs_per_s"] = round(pairs / (ms * 1e-3) / 1e9, 2)
-        stages[name] = st
-    dom = next(iter(stages))
-    roof = {"kernel": dom}
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of each call's kernel(s), from the committed
-    # `ncu --set full` capture of this same workload (profiles/ncu_traffic.json; null for other sizes)
+    # dram__bytes_read.sum + dram__bytes_write.sum per STEP of each stage from the committed `ncu --set full`
+    # capture of this same workload (profiles/ncu_traffic.json, not measured in this run; null for other sizes)
     traffic = {}
-    if (P, W, H) == (P_FULL, W_FULL, H_FULL):
+    if (P, W, H, views, world) == (P_FULL, W_FULL, H_FULL, 8, 1):
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             traffic = {}
-    for name, st in stages.items():
+    stages = {}
+    for name, (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        ms = tot / args.steps  # per step of this rank
+        st = {"ms_per_step": round(ms, 4), "ms_per_render": round(ms / views, 4), "share": round(tot / total_ms, 4),
+              "calls_per_step": n / args.steps}
+        ab = algorithmic_bytes(name, P, M, Cs, D, cpad, views, cnt["nvis_any"], cnt["nlive_any"])
+        if ab is not None:
+            st["GBps"] = round(ab / (ms * 1e-3) / 1e9, 1)
+            st["hbm_frac"] = round(st["GBps"] / hbm, 3)
+            st["algorithmic_MB_per_step"] = round(ab / 1e6, 1)
         if isinstance(traffic.get(name), (int, float)):
-            st["dram_traffic_MB"] = round(traffic[name] / 1e6, 1)
+            st["dram_traffic_MB_per_step"] = round(traffic[name] / 1e6, 1)
+            st["GBps_measured_bytes"] = round(traffic[name] / (ms * 1e-3) / 1e9, 1)
+            st["hbm_frac_measured_bytes"] = round(st["GBps_measured_bytes"] / hbm, 3)
+        if is_blend(name):
+            st["Gpairs_per_s"] = round(pairs / (ms * 1e-3) / 1e9, 2)
+            st["Gblended_pairs_per_s"] = round(blended / (ms * 1e-3) / 1e9, 2)
+        stages[name] = st
+    dom = next(iter(stages))
+    roof = {"kernel": dom}
     if is_blend(dom):
         bwd = dom.endswith("backward")
         lane_ops = (32 + 5 * C) if bwd else (13 + C)
         mufu = 2 if bwd else 1
         peak = min(sms * 128 * f_hz / lane_ops, sms * 16 * f_hz / mufu) / 1e9
         ach = stages[dom]["Gpairs_per_s"]
+        ach_b = stages[dom]["Gblended_pairs_per_s"]
         roof.update({"bound": "fp32_issue", "achieved": ach, "peak": round(peak, 1), "unit": "Gpairs/s",
                      "frac": round(ach / peak, 4), "traffic": traffic.get(dom),
-                     "note": f"pair = sum(ncontrib) = {pairs} per render (SURVEY 8d); peak = min(SMs*128*f/"
-                             f"{lane_ops} lane-ops, SMs*16*f/{mufu} MUFU) at {sms} SMs, f = {f_hz/1e6:.0f} MHz "
-                             f"(clock observed during the run); not an HBM/tensor kernel: DRAM traffic is <10% of "
-                             f"peak (profiles/), so `traffic` is not the limiter"})
+                     # distance to the roof on work that HAS to be executed: only pairs that pass the alpha test need
+                     # the full per-pair arithmetic (the traversed-but-skipped ones are culled per warp)
+                     "frac_blended_pairs": round(ach_b / peak, 4), "achieved_blended": ach_b,
+                     "issue_active_ncu": traffic.get("_issue_active", {}).get(dom),
+                     "note": f"SURVEY 8d: pair = sum(ncontrib) = {pairs} per step of {views} views; blended pairs (pass the "
+                             f"power/alpha tests) = {blended}; peak = min(SMs*128*f/{lane_ops} lane-ops, SMs*16*f/{mufu} "
+                             f"MUFU) at {sms} SMs, f = {f_hz/1e6:.0f} MHz (clock observed during the run). `frac` charges "
+                             f"every traversed pair the full arithmetic and can exceed what the kernel executes (most "
+                             f"traversed pairs are culled per warp); `frac_blended_pairs` charges only pairs that blend "
+                             f"and is the distance to the roof (<= 1).  Not an HBM/tensor kernel: DRAM traffic is <10% "
+                             f"of peak (profiles/); `traffic` and `issue_active_ncu` come from the committed ncu capture "
+                             f"(profiles/ncu_traffic.json), not from this run"})
     else:
         ach = stages[dom].get("GBps", 0.0)
         roof.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
                      "traffic": traffic.get(dom), "note": f"peak: {src}"})
-    # the largest HBM-bound call in the contract's own roofline schema (the dominant call above is issue-bound)
+    # the largest HBM-bound stage in the contract's own roofline schema (the dominant stage above is issue-bound)
     hb = [(n, st) for n, st in stages.items() if "GBps" in st and not is_blend(n)]
     roof_hbm = None
     if hb:
-        n, st = max(hb, key=lambda kv: kv[1]["ms"])
+        n, st = max(hb, key=lambda kv: kv[1]["ms_per_step"])
         roof_hbm = {"kernel": n, "bound": "hbm", "achieved": st["GBps"], "peak": hbm, "unit": "GB/s",
                     "frac": round(st["GBps"] / hbm, 4), "traffic": traffic.get(n),
-                    "note": f"algorithmic bytes {st['algorithmic_MB']} MB per call (DESIGN.md section 5, SURVEY 8d) / "
-                            f"{st['ms']} ms; peak: {src}; traffic = measured DRAM bytes per call (ncu)"}
-    # secondary: the HBM-bound sort (the north star asks for its achieved GB/s)
+                    "achieved_measured_bytes": st.get("GBps_measured_bytes"),
+                    "note": f"algorithmic bytes {st['algorithmic_MB_per_step']} MB per step (DESIGN.md section 5, SURVEY "
+                            f"8d) / {st['ms_per_step']} ms; peak: {src}; traffic = DRAM bytes per step from the committed "
+                            f"ncu capture; achieved_measured_bytes = traffic / time"}
+    # secondary: the sort (the north star asks for its achieved GB/s)
     if "sort_gaussian" in stages:
-        s = stages["sort_gaussian"]
-        s["Gkeys_per_s"] = round(M / (s["ms"] * 1e-3) / 1e9, 3)
-        s["note"] = f"M = {M} keys, 6 onesweep passes over 45 significant bits, 172 B/key algorithmic; peak {hbm} GB/s {src}"
-    return {"roofline": roof, "roofline_hbm": roof_hbm, "stages": stages, "pairs_per_render": pairs, "keys_per_render": M,
-            "gaussians_touching_a_tile": nvis, "gaussians_with_colour_gradient": nlive}
+        sg = stages["sort_gaussian"]
+        sg["Gkeys_per_s"] = round(M / (sg["ms_per_step"] * 1e-3) / 1e9, 3)
+        sg["note"] = (f"M = {M} keys per step ({views} views, one batched sort per view chunk), 4 depth-digit passes over "
+                      f"the emitting Gaussians + tile-digit passes over the keys; GBps uses SURVEY's 172 B/key model, "
+                      f"GBps_measured_bytes the DRAM bytes ncu measured; peak {hbm} GB/s {src}")
+    return {"roofline": roof, "roofline_hbm": roof_hbm, "stages": stages, "pairs_per_step": pairs,
+            "blended_pairs_per_step": blended, "keys_per_step": M, "gaussians_touching_a_tile_any_view": cnt["nvis_any"],
+            "gaussians_with_colour_gradient_any_view": cnt["nlive_any"]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -470,8 +539,8 @@ def cpu_baseline(args, sample=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P, W, H = args.gaussians, args.width, args.height
-    Ps = sample or min(P, 1_000_000)
-    sc = frustum_scene(P, W, H, SIGMA, seed=0, sh_degree=SH_DEG)
+    Ps = sample or P  # the full workload: one render of all P Gaussians (about 15-40 s of CPU work)
+    sc = frustum_scene(P, W, H, args.sigma, seed=0, sh_degree=SH_DEG)
     params = [t[:Ps].clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
     center = sc.cam_center
     G = torch.randn(4, H, W, generator=torch.Generator().manual_seed(1))
@@ -489,10 +558,123 @@ def cpu_baseline(args, sample=None):
     render_once(Api, params, (sc.intr, sc.extr, center), W, H, G)
     dt = time.time() - t0
     scale = P / Ps
+    what = (f"one fwd+bwd render of the full workload ({P} Gaussians at {W}x{H})" if Ps == P else
+            f"one fwd+bwd render of the first {Ps} of the {P} Gaussians at {W}x{H}, value extrapolated x{scale:.1f} "
+            f"linearly in P (the blend cost is not linear in P: a sample, not a measurement of the workload)")
     return {"value": 1.0 / (dt * scale), "unit": "renders/s", "cores": cores, "kind": "port",
-            "sample": f"one fwd+bwd render of the first {Ps} of the {P} Gaussians at {W}x{H} by the CPU oracle "
-                      f"(torch + C/OpenMP blend) in {dt:.1f} s on {cores} threads; value extrapolated x{scale:.0f} "
-                      f"linearly in P"}
+            "sample": f"{what} by the CPU oracle (torch + C/OpenMP blend) in {dt:.1f} s on {cores} threads"}
+
+
+def other_configs(api, dev):
+    """Summary numbers of the BASELINE configs that are not the bench line (bounded: a few seconds each).
+    Parity of these configs is in tests/test_gpu_configs.py; tools/config_bench.py times the reference beside."""
+    import oracle
+    from msplat_b200.scenes import bunny2d_scene, cube_scene, frustum_scene, orbit_cameras
+    res = {}
+
+    def timed(fn, iters=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    try:  # 1: the CPU oracle's own case (10k Gaussians, 256x256, SH3 RGB), vectorised oracle on the host cores
+        sc = cube_scene(10000, 256, 256, seed=0, sh_degree=3)
+        G = torch.randn(3, 256, 256, generator=torch.Generator().manual_seed(1))
+        oracle.steps.build_blend_ref()
+
+        def cpu_once():
+            L = [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
+            uv, depth = oracle.project_point(L[0], sc.intr, sc.extr, 256, 256)
+            vis = (depth != 0).reshape(-1)
+            dirs = L[0] - sc.cam_center
+            dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+            rgb = torch.clamp_min(oracle.compute_sh(L[4], dirs, vis) + 0.5, 0.0)
+            cov = oracle.compute_cov3d(L[1], L[2], vis)
+            conic, radius, tiles = oracle.ewa_project(L[0], cov, sc.intr, sc.extr, uv, 256, 256, vis)
+            ids, tr = oracle.sort_gaussian(uv, depth, 256, 256, radius, tiles)
+            (oracle.alpha_blending(uv, conic, L[3], rgb, ids, tr, 0.0, 256, 256) * G).sum().backward()
+            return int(ids.numel())
+
+        cpu_once()
+        ts = []
+        for _ in range(5):
+            t0 = time.time()
+            M1 = cpu_once()
+            ts.append(time.time() - t0)
+        scd = sc.to(dev)
+        Gd = G.to(dev)
+
+        def gpu_once():
+            L = [t.clone().requires_grad_() for t in (scd.xyz, scd.scale, scd.quat, scd.opacity, scd.shs)]
+            (api.rasterization_sh(*L, scd.intr, scd.extr, 256, 256, 0.0) * Gd).sum().backward()
+
+        res["config1"] = {"what": "10k Gaussians, 256x256, SH3 RGB fwd+bwd", "keys": M1,
+                          "cpu_oracle_renders_per_s": round(1.0 / statistics.median(ts), 3), "cpu_cores": os.cpu_count(),
+                          "ours_ms": round(timed(gpu_once, 20, 3), 4)}
+    except Exception as e:  # pragma: no cover
+        res["config1"] = {"error": repr(e)[:200]}
+    try:  # 2: gs_2d initialisation (sort-dominated)
+        sc = bunny2d_scene(100000, 512, 512, seed=123).to(dev)
+        rgb = torch.sigmoid(torch.rand(100000, 3, generator=torch.Generator().manual_seed(1))).to(dev)
+        target = torch.rand(3, 512, 512, generator=torch.Generator().manual_seed(2)).to(dev)
+        keys = {}
+
+        def once2():
+            L = [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, rgb)]
+            img = api.rasterization(*L, sc.intr, sc.extr, 512, 512, 1.0)
+            torch.nn.functional.smooth_l1_loss(img, target).backward()
+
+        res["config2"] = {"what": "gs_2d initialisation: 100k Gaussians, 512x512 RGB, rasterization() fwd+bwd (M ~ 65.8M keys)",
+                          "ours_ms": round(timed(once2, 5, 2), 4)}
+        del sc, rgb, target
+    except Exception as e:  # pragma: no cover
+        res["config2"] = {"error": repr(e)[:200]}
+    try:  # 4: SH degree 10, 32 channels, 1M Gaussians, 1080p (15.5 GB of coefficients, generated on the device)
+        sc = frustum_scene(1_000_000, 1920, 1080, 2.0, seed=0, with_sh=False).to(dev)
+        gen = torch.Generator(device=dev).manual_seed(3)
+        shs = 0.1 * torch.randn(1_000_000, 32, 121, device=dev, generator=gen)
+        shs[:, :, 0] *= 5.0
+        shs.requires_grad_()
+        G4 = torch.randn(32, 1080, 1920, device=dev, generator=gen)
+        L4 = [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity)] + [shs]
+
+        def once4():
+            for t in L4:
+                t.grad = None
+            (api.rasterization_sh(*L4, sc.intr, sc.extr, 1920, 1080, 0.0) * G4).sum().backward()
+
+        res["config4"] = {"what": "1M Gaussians, 1080p, SH degree 10, 32-channel feature map, fused fwd+bwd",
+                          "sh_elements": int(shs.numel()), "ours_ms": round(timed(once4, 3, 1), 3)}
+        del sc, shs, G4, L4
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        res["config4"] = {"error": repr(e)[:200]}
+    try:  # 5: 6M Gaussians, 4K, 8 of the 64 cameras as one view batch (the full 64-camera step: bench.py --config 5)
+        sc = frustum_scene(P5, W5, H5, SIGMA5, seed=0, sh_degree=3).to(dev)
+        ex = torch.stack(orbit_cameras(VIEWS5)[:8]).to(dev)
+        G5 = torch.randn(4, H5, W5, device=dev)
+        L5 = [t.clone().requires_grad_() for t in (sc.xyz, sc.scale, sc.quat, sc.opacity, sc.shs)]
+
+        def once5():
+            for t in L5:
+                t.grad = None
+            (api.rasterization_sh_views(*L5, sc.intr, ex, W5, H5, 0.0, with_depth=True) * G5).sum().backward()
+
+        ms5 = timed(once5, 2, 1)
+        res["config5"] = {"what": "6M Gaussians, 3840x2160, SH3 RGB+depth: one batch of 8 of the 64 cameras, fwd+bwd",
+                          "ours_ms_per_batch": round(ms5, 3), "ours_ms_per_view": round(ms5 / 8, 3)}
+        del sc, ex, G5, L5
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        res["config5"] = {"error": repr(e)[:200]}
+    return res
 
 
 def run_oracle(args, as_reference=False):
@@ -534,10 +716,24 @@ def main():
     ap.add_argument("--api", default="fused", choices=["fused", "steps"],
                     help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
     ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
-    ap.add_argument("--grad-chunks", type=int, default=3,
+    ap.add_argument("--grad-chunks", type=int, default=2,
                     help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels")
+    ap.add_argument("--view-chunk", type=int, default=0, help="views per batched launch (0 = all views of the rank)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5],
+                    help="BASELINE config: 3 = headline (default), 5 = 6M Gaussians, 4K, 64 cameras strong-scaled over N")
+    ap.add_argument("--sigma", type=float, default=None)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config #1/#2/#4/#5 summary numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.config == 5:
+        if args.gaussians == P_FULL:
+            args.gaussians = P5
+        if (args.width, args.height) == (W_FULL, H_FULL):
+            args.width, args.height = W5, H5
+        args.sigma = SIGMA5 if args.sigma is None else args.sigma
+        if args.view_chunk == 0:
+            args.view_chunk = 8
+    args.sigma = SIGMA if args.sigma is None else args.sigma
     if args.impl == "oracle":
         return run_oracle(args)
     if args.impl == "reference":

@@ -113,6 +113,16 @@ int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* 
                             int P, int views, long long M, int W, int H, int32_t* idx_sorted,
                             int32_t* tile_range, void* ws, size_t ws_bytes, int sm_count, void* stream);
 
+/* Level-1 replacements of the two sort-stage functions of msplat._C, for a maintainer who keeps the
+ * reference's msplat/sort_gaussian.py unchanged (torch.cumsum / torch.sort / torch.gather stay in Python):
+ * computeGaussianKey (src/sort_gaussian.cu:74-113): cumsum [P] = inclusive int32 cumsum of tiles, M =
+ *   cumsum[P-1]; keys [M] int64 = (tile << 32) | depth bits and idx [M] int32, zeroed then filled;
+ * computeTileGaussianRange (src/sort_gaussian.cu:115-142): tile_range [T,2] zeroed then filled. */
+int msb_compute_gaussian_key(const float* uv, const float* depth, const int32_t* radius, const int32_t* cumsum,
+                             int P, long long M, int W, int H, long long* keys, int32_t* idx, void* stream);
+int msb_compute_tile_gaussian_range(const long long* keys_sorted, long long M, int W, int H, int32_t* tile_range,
+                                    void* stream);
+
 /* ---- alpha_blending -----------------------------------------------------------------------
  * replaces alphaBlendingForward / alphaBlendingBackward (src/alpha_blending.cu:248-573)
  * feature [P,C] row-major (the Python-level layout); image [C,H,W]; final_T [H,W];
@@ -130,6 +140,11 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
                            int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
                            const float* dL_dimage, const void* packed, float* dL_duv, float* dL_dconic,
                            float* dL_dopacity, float* dL_dfeature, void* ws, size_t ws_bytes, void* stream);
+
+/* Rebuilds `packed` from the forward's inputs (for a backward entry that does not receive the forward's
+ * workspace, like msplat._C.alpha_blending_backward). */
+int msb_blend_pack(const float* uv, const float* conic, const float* opacity, const float* feature, int P, int C,
+                   void* packed, size_t packed_bytes, void* stream);
 
 /* ---- packed blend (inputs/gradients stay in the blend kernels' packed layout) --------------
  * Same kernels as msb_alpha_blending_fwd/bwd (src/alpha_blending.cu:248-573) without the

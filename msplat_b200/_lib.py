@@ -57,6 +57,10 @@ def _declare(lib):
         "msb_blend_packed_bwd": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, P, I, V]),
         "msb_render_preprocess_fwd": (I, [P] * 7 + [I, I, I, I, I, I, F, F, F, I] + [P] * 8 + [V]),
         "msb_render_preprocess_bwd": (I, [P] * 9 + [I, I, I, I, F, I, I] + [P] * 7 + [V]),
+        # Level-1 drop-ins for msplat._C (integration/_C.py)
+        "msb_compute_gaussian_key": (I, [P, P, P, P, I, LL, I, I, P, P, V]),
+        "msb_compute_tile_gaussian_range": (I, [P, LL, I, I, P, V]),
+        "msb_blend_pack": (I, [P, P, P, P, I, I, P, SZ, V]),
         # view batches
         "msb_sort_num_passes_views": (I, [I, I, I]),
         "msb_sort_workspace_bytes_views": (SZ, [I, I, LL, I, I]),

@@ -705,6 +705,24 @@ int msb_alpha_blending_fwd(const float* uv, const float* conic, const float* opa
     return run_fwd_passes(st, rec, fsrc, Cpad, C, idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib);
 }
 
+// Pack only: rebuilds the `packed` buffer of msb_alpha_blending_fwd from the same inputs.  For callers
+// whose backward entry does not receive the forward's workspace (msplat._C.alpha_blending_backward takes
+// uv / conic / opacity / feature again: integration/_C.py).
+int msb_blend_pack(const float* uv, const float* conic, const float* opacity, const float* feature, int P, int C,
+                   void* packed, size_t packed_bytes, void* stream) {
+    if (P < 0 || C < 0) return set_error(MSB_ERR_ARG, "blend_pack: bad argument");
+    if (P == 0) return MSB_OK;
+    if (!uv || !conic || !opacity || !packed || (C > 0 && !feature)) return set_error(MSB_ERR_ARG, "blend_pack: null pointer");
+    if (packed_bytes < msb_blend_fwd_workspace_bytes(P, C)) return set_error(MSB_ERR_WORKSPACE, "blend_pack: workspace too small");
+    if (reinterpret_cast<uintptr_t>(packed) & 15u) return set_error(MSB_ERR_ARG, "blend_pack: 16-byte alignment");
+    const int Cpad = msb_blend_cpad(C);
+    float4* rec = reinterpret_cast<float4*>(packed);
+    float* featp = (C != Cpad) ? reinterpret_cast<float*>(packed) + (size_t)P * 8 : nullptr;
+    blend_pack_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        P, C, Cpad, reinterpret_cast<const float2*>(uv), conic, opacity, feature, rec, featp);
+    return check_launch("blend_pack");
+}
+
 // Forward on inputs that are already in the packed layout (rec [P,8], featp [P,Cpad] with
 // Cpad = msb_blend_cpad(C)): what msb_render_preprocess_fwd produces.
 // views > 1: a view batch in one grid.  rec [views*P,8], featp [views*P,Cpad], idx_sorted and

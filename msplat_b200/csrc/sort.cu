@@ -926,6 +926,64 @@ int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_i
     return MSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Level-1 drop-in of the two sort-stage functions of msplat._C (integration/_C.py): the reference's
+// Python keeps torch.cumsum / torch.sort / torch.gather between them (msplat/sort_gaussian.py:42-52)
+// ------------------------------------------------------------------------------------------------
+// computeGaussianKeyCUDAKernel (src/sort_gaussian.cu:17-43): key = (tile << 32) | depth bits at slots
+// [cumsum[i-1], ...), rows then columns.  A warp takes 32 Gaussians and writes each footprint cooperatively
+// (the reference: one thread, serially).  Divergences as in the fused sort: depth bits masked to 32 bits,
+// at most cumsum[i] - cumsum[i-1] entries per Gaussian; unwritten slots stay (0, 0) (zeroed by the caller).
+__global__ void __launch_bounds__(256) gaussian_key_kernel(int P, const float2* __restrict__ uv,
+                                                           const float* __restrict__ depth,
+                                                           const int* __restrict__ radius,
+                                                           const int* __restrict__ cumsum, int gx, int gy,
+                                                           long long* __restrict__ keys, int* __restrict__ idx_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int n = 0, start = 0, x0 = 0, y0 = 0, w = 1;
+    unsigned int dbits = 0;
+    if (i < P) {
+        start = i == 0 ? 0 : cumsum[i - 1];
+        const int slots = cumsum[i] - start;
+        n = keygen_count(slots, radius[i], uv[i], gx, gy, x0, y0, w);
+        dbits = __float_as_uint(depth[i]);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, n > 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int bn = __shfl_sync(0xffffffffu, n, src), bstart = __shfl_sync(0xffffffffu, start, src);
+        const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const int bw = __shfl_sync(0xffffffffu, w, src);
+        const unsigned int bd = __shfl_sync(0xffffffffu, dbits, src);
+        const int bi = (int)(i - lane + src);
+        for (int e = lane; e < bn; e += 32) {
+            const int ry = e / bw, rx = e - ry * bw;
+            const long long tile = (long long)(by0 + ry) * gx + bx0 + rx;
+            keys[bstart + e] = (tile << 32) | (long long)bd;
+            idx_out[bstart + e] = bi;
+        }
+    }
+}
+
+// computeTileGaussianRangeCUDAKernel (src/sort_gaussian.cu:45-71) on sorted 64-bit keys; tile_range pre-zeroed
+__global__ void __launch_bounds__(256) tile_range64_kernel(long long M, const long long* __restrict__ keys,
+                                                           int2* __restrict__ tile_range, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int cur = (int)(keys[i] >> 32);
+    if (cur < 0 || cur >= T) return;
+    if (i == 0) tile_range[cur].x = 0;
+    if (i == M - 1) tile_range[cur].y = (int)M;
+    if (i == 0) return;
+    const int prev = (int)(keys[i - 1] >> 32);
+    if (prev != cur) {
+        if (prev >= 0 && prev < T) tile_range[prev].y = (int)i;
+        tile_range[cur].x = (int)i;
+    }
+}
+
 // Number of 8-bit digit passes over the 64-bit key: 4 depth passes (on the Gaussians) plus the
 // tile-id passes (on the duplicates).  A batch of `views` views sorts (view * T + tile) ids.
 int msb_sort_num_passes_views(int W, int H, int views) {
@@ -1060,6 +1118,38 @@ int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* 
     tile_range_kernel<<<(unsigned)((M + 1023) / 1024), 256, 0, st>>>((int)M, tk[L.tpass % 2],
                                                                   reinterpret_cast<int2*>(tile_range), T);
     return check_launch("sort_gaussian/tile_range");
+}
+
+// msplat._C.compute_gaussian_key: cumsum [P] = inclusive int32 cumsum of tiles_touched, M = cumsum[P-1];
+// keys [M] int64 and idx [M] int32 are zeroed and then filled.
+int msb_compute_gaussian_key(const float* uv, const float* depth, const int32_t* radius, const int32_t* cumsum, int P,
+                             long long M, int W, int H, long long* keys, int32_t* idx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P < 0 || M < 0 || W <= 0 || H <= 0) return set_error(MSB_ERR_ARG, "compute_gaussian_key: bad argument");
+    if (M == 0 || P == 0) return MSB_OK;
+    if (!uv || !depth || !radius || !cumsum || !keys || !idx) return set_error(MSB_ERR_ARG, "compute_gaussian_key: null pointer");
+    if (M > (long long)INT32_MAX) return set_error(MSB_ERR_RANGE, "compute_gaussian_key: more than 2^31 - 1 tile intersections");
+    cudaError_t e = cudaMemsetAsync(keys, 0, (size_t)M * sizeof(long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(idx, 0, (size_t)M * sizeof(int32_t), st);
+    if (e != cudaSuccess) return set_error((int)e, "compute_gaussian_key: memset failed");
+    const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
+    gaussian_key_kernel<<<(unsigned)(((long long)P + 255) / 256), 256, 0, st>>>(
+        P, reinterpret_cast<const float2*>(uv), depth, radius, cumsum, gx, gy, keys, idx);
+    return check_launch("compute_gaussian_key");
+}
+
+// msplat._C.compute_tile_gaussian_range: tile_range [T,2] is zeroed and then filled from the sorted keys.
+int msb_compute_tile_gaussian_range(const long long* keys_sorted, long long M, int W, int H, int32_t* tile_range,
+                                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M < 0 || W <= 0 || H <= 0 || !tile_range) return set_error(MSB_ERR_ARG, "compute_tile_gaussian_range: bad argument");
+    const int T = ((W + MSB_TILE - 1) / MSB_TILE) * ((H + MSB_TILE - 1) / MSB_TILE);
+    cudaError_t e = cudaMemsetAsync(tile_range, 0, (size_t)T * 2 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return set_error((int)e, "compute_tile_gaussian_range: memset failed");
+    if (M == 0) return MSB_OK;
+    if (!keys_sorted) return set_error(MSB_ERR_ARG, "compute_tile_gaussian_range: null pointer");
+    tile_range64_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(M, keys_sorted, reinterpret_cast<int2*>(tile_range), T);
+    return check_launch("compute_tile_gaussian_range");
 }
 
 // Phase 2.  idx_sorted[M] (int32) and tile_range[T, 2] (int32) are outputs owned by the caller.
