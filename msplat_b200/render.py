@@ -415,8 +415,10 @@ def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
         n, u = hi - lo, cum[k + 1] - cum[k]
         n4 = (n + 3) // 4 * 4
         flat = torch.empty((11 * n4 + u * F,), dtype=f32, device=dev)
+        # (a slab without a single live Gaussian still needs a valid dL_dshs pointer: no row is ever written)
+        rows = flat[11 * n4:].view(u, F) if u > 0 else torch.empty((1, F), dtype=f32, device=dev)
         outs = (flat[0:3 * n].view(n, 3), flat[3 * n4:3 * n4 + 3 * n].view(n, 3),
-                flat[6 * n4:6 * n4 + 4 * n].view(n, 4), flat[10 * n4:10 * n4 + n], flat[11 * n4:].view(u, F))
+                flat[6 * n4:6 * n4 + 4 * n].view(n, 4), flat[10 * n4:10 * n4 + n], rows)
         if n4 != n:
             flat[:11 * n4].zero_()  # the few padding floats are reduced too
         for c in range(len(chunks)):
@@ -439,7 +441,7 @@ def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
         _lib.call("grad_expand_rows", 1, L.msb_grad_expand_rows, dev, ptr(outs[4]), ptr(row_index[lo:hi]), cum[k],
                   hi - lo, F, ptr(dshs[lo:hi]))
     if ctx.stats is not None:
-        ctx.stats["allreduce_floats"] = sum(int(o[4].numel()) + 11 * (hi - lo) for lo, hi, o in slabs)
+        ctx.stats["allreduce_floats"] = (cum[-1] - cum[0]) * F + 11 * P
         ctx.stats["allreduce_dense_floats"] = P * (11 + F)
     return dxyz, dscale, dquat, dop, dshs
 
