@@ -332,6 +332,19 @@ def run_gpu(args, api, impl):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if args.trace and rank == 0:  # CPU + GPU timeline of three e2e steps (diagnostic; not a measurement)
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    with torch.cuda.stream(copy_stream):
+                        g_dev.copy_(G_host, non_blocking=True)
+                        g_ev = copy_stream.record_event()
+                    ins = (intr_h.to(dev, non_blocking=True), extr_h.to(dev, non_blocking=True),
+                           cent_h.to(dev, non_blocking=True), Staged(g_dev, g_ev))
+                    tot = step(*ins)
+                    loss_host.copy_(tot.reshape(1), non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+            prof.export_chrome_trace(args.trace)
         n = world * V * args.steps
         return ms / args.steps, n / (ms / 1e3), n / (float(t[0]) / 1e3), launches, timing, (t0, t1)
 
@@ -723,6 +736,7 @@ def main():
                     help="BASELINE config: 3 = headline (default), 5 = 6M Gaussians, 4K, 64 cameras strong-scaled over N")
     ap.add_argument("--sigma", type=float, default=None)
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config #1/#2/#4/#5 summary numbers")
+    ap.add_argument("--trace", default=None, help="export a torch.profiler chrome trace of three e2e steps to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.config == 5:

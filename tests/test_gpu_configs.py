@@ -10,7 +10,7 @@ import math
 import pytest
 import torch
 
-from test_gpu_parity import DEV, compare_grads, grad_close, spread
+from test_gpu_parity import DEV, SH_ATOL, compare_grads, grad_close, spread
 from test_gpu_render_sh import steps_pipeline
 
 pytestmark = pytest.mark.gpu
@@ -115,6 +115,9 @@ def _config4_compare(ms, ref_msplat, sc, tag, fused=True):
 
     names = ["dxyz", "dscale", "dquat", "dopacity", "dshs"]
     ref, nf = spread(lambda: run("ref", lambda L: steps_pipeline(ref_msplat, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)), n=1)
+    # dL_dshs and dL_dxyz flow through the degree-10 basis / its derivative: besides the atomics spread, the floor is
+    # the reference's own compute_sh tolerance (SH_ATOL at the tensor's scale, see test_gpu_parity.SH_ATOL)
+    nf = [max(f, SH_ATOL * float(r.abs().max())) if n in ("dxyz", "dshs") else f for n, f, r in zip(names, nf, ref)]
     ours = run("steps", lambda L: steps_pipeline(ms, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False))
     for n, a, b, f in zip(names, ours, ref, nf):
         grad_close(a, b, noise=f, what=f"{tag} steps {n}")

@@ -14,7 +14,7 @@ import torch
 
 import oracle
 from conftest import ROOT
-from test_gpu_parity import DEV, camera, cloud, compare_grads, cpu, grad_close, spread
+from test_gpu_parity import DEV, K_ORACLE, camera, cloud, compare_grads, cpu, grad_close, spread
 
 pytestmark = pytest.mark.gpu
 
@@ -237,7 +237,7 @@ def test_render_sh_vs_oracle(ms):
     assert flips <= 5, f"image err {float(err.max())} on {flips} pixels"
     (img_o * g).sum().backward()
     for n, a, o, f in zip(["xyz", "scale", "quat", "opacity", "shs"], ours, O, nf):
-        grad_close(a, o.grad, noise=f, what=f"render_sh/oracle d{n}", min_frac=1.0 if flips == 0 else 0.999)
+        grad_close(a, o.grad, noise=f, k=K_ORACLE, what=f"render_sh/oracle d{n}", min_frac=1.0 if flips == 0 else 0.999)
 
 
 def test_render_sh_vs_reference_steps(ms, ref_msplat):
