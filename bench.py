@@ -313,6 +313,12 @@ def run_gpu(args, api, impl):
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         g_dev = torch.empty_like(G)
+        # one untimed e2e step: the first one allocates the copy stream's buffers and the pinned staging of the loss
+        with torch.cuda.stream(copy_stream):
+            g_dev.copy_(G_host, non_blocking=True)
+            g_ev = copy_stream.record_event()
+        loss_host.copy_(step(intr_h.to(dev, non_blocking=True), extr_h.to(dev, non_blocking=True),
+                             cent_h.to(dev, non_blocking=True), Staged(g_dev, g_ev)).reshape(1), non_blocking=True)
         barrier_sync(world)
         e0.record()
         # The 33 MB cotangent is copied every step on a copy stream into a reused device buffer, under the

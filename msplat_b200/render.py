@@ -48,6 +48,9 @@ _tls = threading.local()
 # views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
 VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
 M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
+# forward blend leaves a byte per list entry (which warps blended it) for the backward blend; MSB_TOUCH=0 makes the
+# backward pass repeat the footprint test instead (A/B switch, same results)
+USE_TOUCH = os.environ.get("MSB_TOUCH", "1") != "0"
 
 
 @contextmanager
@@ -140,6 +143,14 @@ def rasterization_sh_views(
     return images
 
 
+def _m_guess() -> dict:
+    """per-thread memo: tile intersections per view chunk of the previous call with the same shape"""
+    g = getattr(_tls, "m_guess", None)
+    if g is None:
+        g = _tls.m_guess = {}
+    return g
+
+
 def _resolve_group(grad_sync):
     """-> process group to all-reduce over, a custom reducer, or None when there is nothing to do."""
     import torch.distributed as dist
@@ -212,9 +223,9 @@ class _RenderSHViews(torch.autograd.Function):
                                "pass a smaller view_chunk")
         f32, i32 = torch.float32, torch.int32
         need_grad = any(ctx.needs_input_grad[:7])
+        overlap = _overlap()
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
-            images = torch.empty((B, C, H, W), dtype=f32, device=dev)
             rec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
             featp = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
             uv = torch.empty((B, Pp, 2), dtype=f32, device=dev)
@@ -224,24 +235,8 @@ class _RenderSHViews(torch.autograd.Function):
             if Pp != P:  # padding rows take no part in the sort
                 tiles[:, P:].zero_()
                 radius[:, P:].zero_()
-            final_T = torch.empty((B, H, W), dtype=f32, device=dev)
-            ncontrib = torch.empty((B, H, W), dtype=i32, device=dev)
-            tr = torch.empty((B * T, 2), dtype=i32, device=dev)
             totals = _lib.pinned_i64(dev, B)
             total_dev = torch.empty((B,), dtype=torch.int64, device=dev)
-            side = _side_stream(dev) if _overlap() else None
-            grec = gfeat = cleared = None
-            if need_grad and P > 0 and C > 0:
-                # packed gradient buffers of the backward blend: cleared now, on the side stream, under the
-                # sort / forward blend (the 48 B per Gaussian and view memset leaves the critical path)
-                grec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
-                gfeat = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
-                with torch.cuda.stream(side if side is not None else main):
-                    if side is not None:
-                        side.wait_stream(main)
-                    grec.zero_()
-                    gfeat.zero_()
-                    cleared = side.record_event() if side is not None else None
             # phase A: per-Gaussian preprocess of every chunk (M per view accumulated in-kernel), ONE host sync
             for b0, nb in chunks:
                 _lib.call("render_preprocess_forward", 1 if P else 0, L.msb_render_preprocess_fwd_views, dev, ptr(x),
@@ -250,18 +245,54 @@ class _RenderSHViews(torch.autograd.Function):
                           ptr(uv[b0]), ptr(depth[b0]), ptr(radius[b0]), ptr(tiles[b0]), ptr(total_dev[b0:]))
             totals[:B].copy_(total_dev, non_blocking=True)  # one device->host copy for the whole batch
             done = main.record_event()
+            # while the device works on phase A, the host prepares everything phase B needs: output tensors, the
+            # cleared packed-gradient buffers of the backward blend, and (sized from the previous call with the
+            # same shape) the sort's outputs and workspace -- so that nothing but the launches follows the sync
+            images = torch.empty((B, C, H, W), dtype=f32, device=dev)
+            final_T = torch.empty((B, H, W), dtype=f32, device=dev)
+            ncontrib = torch.empty((B, H, W), dtype=i32, device=dev)
+            tr = torch.empty((B * T, 2), dtype=i32, device=dev)
+            side = _side_stream(dev) if overlap else None
+            grec = gfeat = cleared = None
+            if need_grad and P > 0 and C > 0:
+                # cleared on the side stream, under the preprocess / sort / forward blend (the 48 B per Gaussian and
+                # view memset leaves the critical path)
+                grec = torch.empty((B, Pp, 8), dtype=f32, device=dev)
+                gfeat = torch.empty((B, Pp, cpad), dtype=f32, device=dev)
+                with torch.cuda.stream(side if side is not None else main):
+                    if side is not None:
+                        side.wait_stream(main)
+                    grec.zero_()
+                    gfeat.zero_()
+                    cleared = side.record_event() if side is not None else None
+            guess_key = (torch.device(dev).index, P, W, H, tuple(chunks))
+            guess = _m_guess().get(guess_key)
+            spec = None
+            if guess is not None:
+                spec = [(torch.empty((mc,), dtype=i32, device=dev),
+                         torch.empty((L.msb_sort_workspace_bytes_views(Pp, nb, mc, W, H),), dtype=torch.uint8, device=dev))
+                        for (b0, nb), mc in zip(chunks, guess)]
             done.synchronize()
             Ms = [int(totals[b]) for b in range(B)]
+            chunks0 = chunks
             chunks = _split_for_sort(chunks, Ms)  # raises before anything else is queued
+            if chunks != chunks0:
+                spec = None
+            # next call: capacity = this call's M per chunk + 6 % (training changes M slowly)
+            _m_guess()[guess_key] = [int(sum(Ms[b0:b0 + nb]) * 1.0625) + 4096 for b0, nb in chunks0]
             # phase B: one sort (side stream when several chunks overlap) + one blend grid per chunk
             two_stream = side is not None and len(chunks) > 1
             if two_stream:
                 side.wait_stream(main)  # the per-view tensors were produced on `main`
-            ids_all, keep = [], []
-            for b0, nb in chunks:
+            ids_all, touch_all, keep = [], [], []
+            for k, (b0, nb) in enumerate(chunks):
                 M = sum(Ms[b0:b0 + nb])
-                ids = torch.empty((M,), dtype=i32, device=dev)
-                ws2 = torch.empty((L.msb_sort_workspace_bytes_views(Pp, nb, M, W, H),), dtype=torch.uint8, device=dev)
+                if spec is not None and M <= spec[k][0].numel():
+                    ids, ws2 = spec[k][0][:M], spec[k][1]
+                else:
+                    ids = torch.empty((M,), dtype=i32, device=dev)
+                    ws2 = torch.empty((L.msb_sort_workspace_bytes_views(Pp, nb, M, W, H),), dtype=torch.uint8,
+                                      device=dev)
                 nk = L.msb_sort_num_passes_views(W, H, nb) + 4 if (M > 0 and P > 0) else 0  # + keygen, offsets, duplicate, ranges
                 with torch.cuda.stream(side if two_stream else main):
                     _lib.call("sort_gaussian", nk, L.msb_sort_gaussian_views, dev, ptr(uv[b0]), ptr(depth[b0]),
@@ -269,10 +300,13 @@ class _RenderSHViews(torch.autograd.Function):
                               ws2.numel(), _lib.sm_count(dev))
                     if two_stream:
                         main.wait_event(side.record_event())
+                # forward state for the backward blend: which warps of a tile's CTA blended which list entry
+                touch = torch.empty((M,), dtype=torch.uint8, device=dev) if (need_grad and USE_TOUCH) else None
                 _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd_views, dev, ptr(rec[b0]),
                           ptr(featp[b0]), ptr(ids), ptr(tr[b0 * T:]), bg, C, W, H, nb, ptr(images[b0]),
-                          ptr(final_T[b0]), ptr(ncontrib[b0]))
+                          ptr(final_T[b0]), ptr(ncontrib[b0]), ptr(touch), M)
                 ids_all.append(ids)
+                touch_all.append(touch)
                 keep.append(ws2)  # alive until both streams are joined (allocated on `main`)
             # all side-stream sorts are ordered before the last blend, hence before anything the caller enqueues
             del keep, uv, depth
@@ -287,7 +321,9 @@ class _RenderSHViews(torch.autograd.Function):
         ctx.has_ndc = ndc is not None
         ctx.stats = stats
         ctx.gbuf = (grec, gfeat, cleared)
+        ctx.touch = touch_all
         ctx.gclean = True
+        ctx.overlap = overlap  # backward runs on autograd's thread: the caller's serialised() does not reach it
         ctx.save_for_backward(x, s, q, sh, I, E, rec, featp, tiles, tr, final_T, ncontrib, *ids_all)
         ctx.mark_non_differentiable(radii)
         return images, radii
@@ -333,7 +369,7 @@ class _RenderSHViews(torch.autograd.Function):
                 b0, nb = chunks[k]
                 _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd_views, dev, ptr(rec[b0]),
                           ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[b0 * T:]), bg, Pp, C, W, H, nb, ptr(final_T[b0]),
-                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
+                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1, ptr(ctx.touch[k]))
 
             def pre_bwd(k, lo, hi, accumulate, outs, row_index=None, row_base=0):
                 """fused preprocess backward of chunk k for the Gaussians [lo, hi)"""
@@ -353,7 +389,7 @@ class _RenderSHViews(torch.autograd.Function):
                 dop = torch.empty((P,), dtype=f32, device=dev)
                 dshs = torch.empty_like(sh)
                 outs = (dxyz, dscale, dquat, dop, dshs)
-                side = _side_stream(dev) if (_overlap() and len(chunks) > 1) else None
+                side = _side_stream(dev) if (ctx.overlap and len(chunks) > 1) else None
                 if side is not None:
                     side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
                 for k in range(len(chunks)):

@@ -114,7 +114,7 @@ def _config4_compare(ms, ref_msplat, sc, tag, fused=True):
         return grads
 
     names = ["dxyz", "dscale", "dquat", "dopacity", "dshs"]
-    ref, nf = spread(lambda: run("ref", lambda L: steps_pipeline(ref_msplat, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)), n=1)
+    ref, nf = spread(lambda: run("ref", lambda L: steps_pipeline(ref_msplat, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False)), n=2)
     # dL_dshs and dL_dxyz flow through the degree-10 basis / its derivative: besides the atomics spread, the floor is
     # the reference's own compute_sh tolerance (SH_ATOL at the tensor's scale, see test_gpu_parity.SH_ATOL)
     nf = [max(f, SH_ATOL * float(r.abs().max())) if n in ("dxyz", "dshs") else f for n, f, r in zip(names, nf, ref)]
