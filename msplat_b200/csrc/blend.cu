@@ -105,7 +105,7 @@ __device__ __forceinline__ void stage_issue(Stage<CH, B>& st, int slot, int id, 
 // that actually blend (pass the power / alpha tests before termination) into `image` reinterpreted as int32
 // [views,H,W] -- the "blended pairs" the roofline of the blend kernels is computed on.
 template <int CH, bool COUNT = false>
-__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
+__global__ void __launch_bounds__(BL_NT, CH == 4 ? 8 : 1) blend_fwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
