@@ -161,18 +161,14 @@ int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* id
                          const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream);
 /* View batch in one grid (blockIdx.z = view): rec [views*P,8], featp [views*P,Cpad], idx_sorted and
  * tile_range [views*T,2] from msb_sort_gaussian_views; image / dL_dimage [views,C,H,W], final_T /
- * ncontrib [views,H,W]; grec [views*P,8], gfeat [views*P,Cpad] (P = rows per view).
- * touch (optional, [M] bytes, M = entries of idx_sorted): forward state for the backward pass -- bit w of
- * touch[i] = warp w of the tile's CTA (8x4 pixels) blended list entry i in at least one pixel; the backward
- * call visits exactly those (entry, warp) pairs instead of repeating the footprint and alpha tests for entries
- * that only cover terminated pixels.  NULL on both sides = footprint test (same results). */
+ * ncontrib [views,H,W]; grec [views*P,8], gfeat [views*P,Cpad] (P = rows per view). */
 int msb_blend_packed_fwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
                                const int32_t* tile_range, float bg, int C, int W, int H, int views, float* image,
-                               float* final_T, int32_t* ncontrib, uint8_t* touch, long long M, void* stream);
+                               float* final_T, int32_t* ncontrib, void* stream);
 int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
                                const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
                                const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
-                               float* gfeat, int already_zero, const uint8_t* touch, void* stream);
+                               float* gfeat, int already_zero, void* stream);
 
 /* ---- fused SH render preprocess ------------------------------------------------------------
  * One forward / one backward kernel for the whole per-Gaussian part of an SH-coloured render:

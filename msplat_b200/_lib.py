@@ -65,8 +65,8 @@ def _declare(lib):
         "msb_sort_num_passes_views": (I, [I, I, I]),
         "msb_sort_workspace_bytes_views": (SZ, [I, I, LL, I, I]),
         "msb_sort_gaussian_views": (I, [P, P, P, P, I, I, LL, I, I, P, P, P, SZ, I, V]),
-        "msb_blend_packed_fwd_views": (I, [P, P, P, P, F, I, I, I, I, P, P, P, P, LL, V]),
-        "msb_blend_packed_bwd_views": (I, [P, P, P, P, F, I, I, I, I, I, P, P, P, P, P, I, P, V]),
+        "msb_blend_packed_fwd_views": (I, [P, P, P, P, F, I, I, I, I, P, P, P, V]),
+        "msb_blend_packed_bwd_views": (I, [P, P, P, P, F, I, I, I, I, I, P, P, P, P, P, I, V]),
         "msb_blend_packed_count": (I, [P, P, P, I, I, I, P, V]),
         "msb_render_preprocess_fwd_views": (I, [P] * 7 + [I, I, I, LL, I, I, I, I, I, F, F, F, I] + [P] * 7 + [V]),
         "msb_render_preprocess_bwd_views": (I, [P] * 6 + [I] + [P] * 4 + [I, I, I, LL, I, I, I, F, I, I] + [P] * 7 + [V]),

@@ -105,23 +105,16 @@ __device__ __forceinline__ void stage_issue(Stage<CH, B>& st, int slot, int id, 
 // that actually blend (pass the power / alpha tests before termination) into `image` reinterpreted as int32
 // [views,H,W] -- the "blended pairs" the roofline of the blend kernels is computed on.
 template <int CH, bool COUNT = false>
-__global__ void __launch_bounds__(BL_NT, CH == 4 ? 8 : 1) blend_fwd_kernel(const float4* __restrict__ rec,
+__global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
                                                           const int2* __restrict__ tile_range, float bg,
                                                           int c_valid, int W, int H, int write_aux,
                                                           float* __restrict__ final_T, int* __restrict__ ncontrib,
-                                                          float* __restrict__ image, long long img_vstride,
-                                                          unsigned char* __restrict__ touch) {
+                                                          float* __restrict__ image, long long img_vstride) {
     extern __shared__ __align__(16) unsigned char bl_raw[];
     Stage<CH>* stages = reinterpret_cast<Stage<CH>*>(bl_raw);
-    // touch (optional, [M] bytes, pre-zeroed): bit w of touch[list position] = "some pixel of warp w's 8x4 block
-    // passed the power / alpha tests for this entry".  Exactly the (entry, warp) visits the backward kernel has
-    // work for: it visits those and nothing else, instead of repeating the footprint test and evaluating alpha
-    // for entries that only cover pixels which had already terminated.
-    __shared__ unsigned int s_touch[2][BL_BATCH / 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 2 * (BL_BATCH / 4)) (&s_touch[0][0])[tid] = 0u;
     const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
     // blockIdx.z = view of a view batch: tile ids, Gaussian ids and tile ranges are those of the batch's
     // single sort (view * T + tile, view * P + index); images / final_T / ncontrib are [views, ...]
@@ -151,23 +144,9 @@ __global__ void __launch_bounds__(BL_NT, CH == 4 ? 8 : 1) blend_fwd_kernel(const
         cp_async_commit();
         if (BL_BATCH + tid < n) id_next = ids[range.x + BL_BATCH + tid];
     }
-    // batch bb's touch bytes -> global, buffer cleared for batch bb + 2 (threads 0..63 own one word each)
-    auto touch_flush = [&](int bb) {
-        if (tid < BL_BATCH / 4) {
-            const unsigned int w4 = s_touch[bb & 1][tid];
-            s_touch[bb & 1][tid] = 0u;
-            const int e0 = bb * BL_BATCH + 4 * tid;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (e0 + k < n) touch[(long long)range.x + e0 + k] = (unsigned char)(w4 >> (8 * k));
-        }
-    };
-    int pending = -1;  // batch whose touch bytes still sit in shared memory (uniform across the CTA)
     for (int b = 0; b < nb; ++b) {
         cp_async_wait<0>();
         if (__syncthreads_and(done)) break;
-        if (touch != nullptr && pending >= 0) touch_flush(pending);
-        pending = b;
         if (b + 1 < nb) {
             if ((b + 1) * BL_BATCH + tid < n)
                 stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
@@ -197,8 +176,6 @@ __global__ void __launch_bounds__(BL_NT, CH == 4 ? 8 : 1) blend_fwd_kernel(const
                 const float alpha = fmin_ftz(fmul(r1.y, G), kAlphaMax);
                 const bool ok = !done && !(power > 0.0f) && !(alpha < kAlphaMin);
                 if (!__any_sync(0xffffffffu, ok)) continue;  // ~1 visit in 5: box hit, but no pixel of the warp blends
-                if (touch != nullptr && lane == 0)
-                    atomicOr(&s_touch[b & 1][j >> 2], 1u << (warp + 8 * (j & 3)));
                 const float nT = fmul(T, fadd(-alpha, 1.0f));
                 const bool term = ok && (nT < kTmin);  // alpha_blending.cu:90-94: entry not blended
                 const bool blend = ok && !term;
@@ -225,10 +202,6 @@ __global__ void __launch_bounds__(BL_NT, CH == 4 ? 8 : 1) blend_fwd_kernel(const
         }
     }
     cp_async_wait<0>();
-    if (touch != nullptr) {
-        __syncthreads();  // every warp is done with the last processed batch
-        if (pending >= 0) touch_flush(pending);
-    }
     if (inside) {
         const long long hw = (long long)H * W;
         const long long pix = (long long)py * W + px;
@@ -361,10 +334,7 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
     __syncwarp();
 }
 
-// MASK: the forward pass left, per list entry, the set of warps with work (touch, see blend_fwd_kernel): a warp
-// visits exactly those entries.  Without it (callers that cannot keep forward state, e.g. the pybind11-shaped
-// msplat._C.alpha_blending_backward) the warps repeat the footprint test of the forward pass.
-template <int CH, int B, int MINB, bool MASK>
+template <int CH, int B, int MINB>
 __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __restrict__ rec,
                                                           const float* __restrict__ featp, int fstride, int foff,
                                                           const int* __restrict__ ids,
@@ -375,7 +345,7 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
                                                           const float* __restrict__ dL_dimage,
                                                           long long img_vstride,
                                                           float* __restrict__ grec, float* __restrict__ gfeat,
-                                                          int geom_grads, const unsigned char* __restrict__ touch) {
+                                                          int geom_grads) {
     extern __shared__ __align__(16) unsigned char bl_raw[];
     using L = Bwd3<CH, B>;
     Stage<CH, B>* stages = reinterpret_cast<Stage<CH, B>*>(bl_raw);
@@ -383,7 +353,6 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
     float* s_dpix = reinterpret_cast<float*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES);
     int* s_q = reinterpret_cast<int*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES + L::DPIX_BYTES);
     __shared__ int s_id[2 * B];  // [2][B] Gaussian ids of the staged slots
-    __shared__ unsigned char s_tch[MASK ? 2 * B : 4];  // [2][B] touch bytes of the staged slots
     __shared__ int s_max[BL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gxt = (W + MSB_TILE - 1) / MSB_TILE;
@@ -443,19 +412,14 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
 
     // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
     int id_next = 0;
-    unsigned char tch_next = 0;
     if (nb > 0) {
         if (tid < B && tid < maxc) {
             const int id = ids[range.x + maxc - 1 - tid];
             s_id[tid] = id;
-            if (MASK) s_tch[tid] = touch[(long long)range.x + maxc - 1 - tid];
             stage_issue(stages[0], tid, id, rec, featp, fstride, foff);
         }
         cp_async_commit();
-        if (tid < B && B + tid < maxc) {
-            id_next = ids[range.x + maxc - 1 - (B + tid)];
-            if (MASK) tch_next = touch[(long long)range.x + maxc - 1 - (B + tid)];
-        }
+        if (tid < B && B + tid < maxc) id_next = ids[range.x + maxc - 1 - (B + tid)];
     }
     for (int b = 0; b < nb; ++b) {
         cp_async_wait<0>();
@@ -463,14 +427,10 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
         if (b + 1 < nb) {
             if (tid < B && (b + 1) * B + tid < maxc) {
                 s_id[((b + 1) & 1) * B + tid] = id_next;
-                if (MASK) s_tch[((b + 1) & 1) * B + tid] = tch_next;
                 stage_issue(stages[(b + 1) & 1], tid, id_next, rec, featp, fstride, foff);
             }
             cp_async_commit();
-            if (tid < B && (b + 2) * B + tid < maxc) {
-                id_next = ids[range.x + maxc - 1 - ((b + 2) * B + tid)];
-                if (MASK) tch_next = touch[(long long)range.x + maxc - 1 - ((b + 2) * B + tid)];
-            }
+            if (tid < B && (b + 2) * B + tid < maxc) id_next = ids[range.x + maxc - 1 - ((b + 2) * B + tid)];
         }
         const Stage<CH, B>& st = stages[b & 1];
         const int* sid = s_id + (b & 1) * B;
@@ -480,14 +440,9 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
         for (int k0 = 0; k0 < bcnt; k0 += 32) {
             bool hit = false;
             if (k0 + lane < bcnt) {
-                if (MASK) {
-                    hit = ((s_tch[(b & 1) * B + k0 + lane] >> warp) & 1u) != 0u;
-                } else {
-                    const float4 r0 = st.rec[2 * (k0 + lane)];
-                    const float4 r1 = st.rec[2 * (k0 + lane) + 1];
-                    hit = !cull_miss(r0.x, r0.y, r1.z, r1.w, wx0, wy0, 8.0f, 4.0f);
-                }
-                hit = hit && (pos0 - (k0 + lane) < wmax);
+                const float4 r0 = st.rec[2 * (k0 + lane)];
+                const float4 r1 = st.rec[2 * (k0 + lane) + 1];
+                hit = !cull_miss(r0.x, r0.y, r1.z, r1.w, wx0, wy0, 8.0f, 4.0f) && (pos0 - (k0 + lane) < wmax);
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             // alpha of a pair (alpha_blending.cu:190-203); the pos < lc test is :185-187
@@ -568,8 +523,7 @@ static inline int pick_bwd_ch(int rem) { return rem >= 16 ? 16 : rem > 4 ? 8 : 4
 template <int CH>
 static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, int write_aux,
-                      float* final_T, int* ncontrib, float* image, long long img_vstride,
-                      unsigned char* touch = nullptr) {
+                      float* final_T, int* ncontrib, float* image, long long img_vstride) {
     const size_t smem = 2 * sizeof(Stage<CH>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(blend_fwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -577,7 +531,7 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
         if (e != cudaSuccess) return set_error((int)e, "alpha_blending_fwd: cudaFuncSetAttribute failed");
     }
     blend_fwd_kernel<CH><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, write_aux,
-                                                    final_T, ncontrib, image, img_vstride, touch);
+                                                    final_T, ncontrib, image, img_vstride);
     return check_launch("alpha_blending_fwd");
 }
 
@@ -593,41 +547,29 @@ static int blend_bwd_cfg() {
     return v;
 }
 
-template <int CH, int B, int MINB, bool MASK>
-static int launch_bwd_cfg2(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
-                           const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
-                           const int* ncontrib, const float* dL_dimage, long long img_vstride, float* grec, float* gfeat,
-                           int geom, const unsigned char* touch) {
-    const size_t smem = Bwd3<CH, B>::SMEM;
-    if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, B, MINB, MASK>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
-    }
-    blend_bwd_kernel<CH, B, MINB, MASK><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W,
-                                                                   H, final_T, ncontrib, dL_dimage, img_vstride, grec,
-                                                                   gfeat, geom, touch);
-    return check_launch("alpha_blending_bwd");
-}
-
 template <int CH, int B, int MINB>
 static int launch_bwd_cfg(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                           const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
                           const int* ncontrib, const float* dL_dimage, long long img_vstride, float* grec, float* gfeat,
-                          int geom, const unsigned char* touch) {
-    return touch != nullptr
-               ? launch_bwd_cfg2<CH, B, MINB, true>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T,
-                                                    ncontrib, dL_dimage, img_vstride, grec, gfeat, geom, touch)
-               : launch_bwd_cfg2<CH, B, MINB, false>(grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
-                                                     final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat, geom, touch);
+                          int geom) {
+    const size_t smem = Bwd3<CH, B>::SMEM;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel<CH, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "alpha_blending_bwd: cudaFuncSetAttribute failed");
+    }
+    blend_bwd_kernel<CH, B, MINB><<<grid, BL_NT, smem, st>>>(rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H,
+                                                             final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat,
+                                                             geom);
+    return check_launch("alpha_blending_bwd");
 }
 
 template <int CH>
 static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float* featp, int fstride, int foff,
                       const int* ids, const int2* tr, float bg, int c_valid, int W, int H, const float* final_T,
                       const int* ncontrib, const float* dL_dimage, long long img_vstride, float* grec, float* gfeat,
-                      int geom, const unsigned char* touch) {
-#define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat, geom, touch
+                      int geom) {
+#define MSB_BWD_ARGS grid, st, rec, featp, fstride, foff, ids, tr, bg, c_valid, W, H, final_T, ncontrib, dL_dimage, img_vstride, grec, gfeat, geom
     if constexpr (CH == 4) {
         switch (blend_bwd_cfg()) {
             case 1: return launch_bwd_cfg<CH, 128, 3>(MSB_BWD_ARGS);
@@ -647,7 +589,7 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float4* rec, const float
 // views > 1: one grid for a whole view batch (blockIdx.z = view), image [views, C, H, W]
 static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H, float* image,
-                          float* final_T, int32_t* ncontrib, int views = 1, unsigned char* touch = nullptr) {
+                          float* final_T, int32_t* ncontrib, int views = 1) {
     const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE, views);
     const long long vs = (long long)C * H * W;
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
@@ -658,22 +600,21 @@ static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
         const int c_valid = max(0, min(ch, C - c0));
         float* img = image ? image + (size_t)c0 * H * W : nullptr;
         int rc;
-        unsigned char* tch = first ? touch : nullptr;  // the geometry is the same in every channel pass
         if (C == 0) {  // geometry-only pass: stage rec twice (no feature rows exist)
             rc = launch_fwd<4>(grid, st, rec, reinterpret_cast<const float*>(rec), 8, 0, idx_sorted, tr, bg, 0, W, H, 1,
-                               final_T, ncontrib, img, vs, tch);
+                               final_T, ncontrib, img, vs);
         } else if (ch == 32) {
             rc = launch_fwd<32>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img, vs, tch);
+                                ncontrib, img, vs);
         } else if (ch == 16) {
             rc = launch_fwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                                ncontrib, img, vs, tch);
+                                ncontrib, img, vs);
         } else if (ch == 8) {
             rc = launch_fwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img, vs, tch);
+                               ncontrib, img, vs);
         } else {
             rc = launch_fwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, first, final_T,
-                               ncontrib, img, vs, tch);
+                               ncontrib, img, vs);
         }
         if (rc) return rc;
         c0 += ch;
@@ -686,7 +627,7 @@ static int run_fwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
 static int run_bwd_passes(cudaStream_t st, const float4* rec, const float* fsrc, int Cpad, int C,
                           const int32_t* idx_sorted, const int32_t* tile_range, float bg, int W, int H,
                           const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
-                          float* gfeat, int views = 1, const unsigned char* touch = nullptr) {
+                          float* gfeat, int views = 1) {
     const dim3 grid((W + MSB_TILE - 1) / MSB_TILE, (H + MSB_TILE - 1) / MSB_TILE, views);
     const long long vs = (long long)C * H * W;
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
@@ -700,13 +641,13 @@ static int run_bwd_passes(cudaStream_t st, const float4* rec, const float* fsrc,
         // reference does the same, alpha_blending.cu:436-567)
         if (ch == 16)
             rc = launch_bwd<16>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                                dimg, vs, grec, gfeat, 1, touch);
+                                dimg, vs, grec, gfeat, 1);
         else if (ch == 8)
             rc = launch_bwd<8>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, vs, grec, gfeat, 1, touch);
+                               dimg, vs, grec, gfeat, 1);
         else
             rc = launch_bwd<4>(grid, st, rec, fsrc, Cpad, c0, idx_sorted, tr, bg, c_valid, W, H, final_T, ncontrib,
-                               dimg, vs, grec, gfeat, 1, touch);
+                               dimg, vs, grec, gfeat, 1);
         if (rc) return rc;
         c0 += ch;
     }
@@ -786,22 +727,17 @@ int msb_blend_pack(const float* uv, const float* conic, const float* opacity, co
 // Cpad = msb_blend_cpad(C)): what msb_render_preprocess_fwd produces.
 // views > 1: a view batch in one grid.  rec [views*P,8], featp [views*P,Cpad], idx_sorted and
 // tile_range [views*T,2] from msb_sort_gaussian_views; image [views,C,H,W], final_T / ncontrib [views,H,W].
-// touch (optional, [M] bytes, M = entries of idx_sorted): written for msb_blend_packed_bwd_views (zeroed here first).
 int msb_blend_packed_fwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
                                const int32_t* tile_range, float bg, int C, int W, int H, int views, float* image,
-                               float* final_T, int32_t* ncontrib, uint8_t* touch, long long M, void* stream) {
+                               float* final_T, int32_t* ncontrib, void* stream) {
     // rec / featp may be NULL for an empty cloud (every tile range is then (0, 0))
     if (C < 0 || W <= 0 || H <= 0 || views <= 0 || views > 65535 || !tile_range || !final_T || !ncontrib ||
         (C > 0 && !image))
         return set_error(MSB_ERR_ARG, "blend_packed_fwd: bad argument");
     if ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(featp)) & 15u)
         return set_error(MSB_ERR_ARG, "blend_packed_fwd: 16-byte alignment");
-    if (touch != nullptr && M > 0) {
-        cudaError_t e = cudaMemsetAsync(touch, 0, (size_t)M, (cudaStream_t)stream);
-        if (e != cudaSuccess) return set_error((int)e, "blend_packed_fwd: memset failed");
-    }
     return run_fwd_passes((cudaStream_t)stream, reinterpret_cast<const float4*>(rec), featp, msb_blend_cpad(C), C,
-                          idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib, views, touch);
+                          idx_sorted, tile_range, bg, W, H, image, final_T, ncontrib, views);
 }
 // Diagnostic (bench.py): blended [views,H,W] int32 = list entries that blend at each pixel.
 int msb_blend_packed_count(const float* rec, const int32_t* idx_sorted, const int32_t* tile_range, int W, int H,
@@ -812,7 +748,7 @@ int msb_blend_packed_count(const float* rec, const int32_t* idx_sorted, const in
     // features are not needed: the records are staged twice (as in the C == 0 pass of run_fwd_passes)
     blend_fwd_kernel<4, true><<<grid, BL_NT, 2 * sizeof(Stage<4>), (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(rec), rec, 8, 0, idx_sorted, reinterpret_cast<const int2*>(tile_range), 0.f, 0,
-        W, H, 0, nullptr, nullptr, reinterpret_cast<float*>(blended), 0, nullptr);
+        W, H, 0, nullptr, nullptr, reinterpret_cast<float*>(blended), 0);
     return check_launch("blend_packed_count");
 }
 
@@ -820,7 +756,7 @@ int msb_blend_packed_fwd(const float* rec, const float* featp, const int32_t* id
                          float bg, int C, int W, int H, float* image, float* final_T, int32_t* ncontrib,
                          void* stream) {
     return msb_blend_packed_fwd_views(rec, featp, idx_sorted, tile_range, bg, C, W, H, 1, image, final_T, ncontrib,
-                                      nullptr, 0, stream);
+                                      stream);
 }
 
 // Backward.  `packed` is the buffer produced by the forward call on the same inputs.
@@ -857,20 +793,20 @@ int msb_alpha_blending_bwd(const float* feature, const int32_t* idx_sorted, cons
 int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
                                const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
                                const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
-                               float* gfeat, int already_zero, const uint8_t* touch, void* stream);
+                               float* gfeat, int already_zero, void* stream);
 int msb_blend_packed_bwd(const float* rec, const float* featp, const int32_t* idx_sorted, const int32_t* tile_range,
                          float bg, int P, int C, int W, int H, const float* final_T, const int32_t* ncontrib,
                          const float* dL_dimage, float* grec, float* gfeat, int already_zero, void* stream) {
     return msb_blend_packed_bwd_views(rec, featp, idx_sorted, tile_range, bg, P, C, W, H, 1, final_T, ncontrib,
-                                      dL_dimage, grec, gfeat, already_zero, nullptr, stream);
+                                      dL_dimage, grec, gfeat, already_zero, stream);
 }
 
 // View batch (see msb_blend_packed_fwd_views): P = Gaussians per view; grec [views*P,8], gfeat [views*P,Cpad],
-// dL_dimage [views,C,H,W]; touch (optional) = the mask the forward call wrote for the same idx_sorted.
+// dL_dimage [views,C,H,W].
 int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32_t* idx_sorted,
                                const int32_t* tile_range, float bg, int P, int C, int W, int H, int views,
                                const float* final_T, const int32_t* ncontrib, const float* dL_dimage, float* grec,
-                               float* gfeat, int already_zero, const uint8_t* touch, void* stream) {
+                               float* gfeat, int already_zero, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (P < 0 || C < 0 || W <= 0 || H <= 0 || views <= 0 || views > 65535)
         return set_error(MSB_ERR_ARG, "blend_packed_bwd: bad argument");
@@ -884,7 +820,7 @@ int msb_blend_packed_bwd_views(const float* rec, const float* featp, const int32
         if (e != cudaSuccess) return set_error((int)e, "blend_packed_bwd: memset failed");
     }
     return run_bwd_passes(st, reinterpret_cast<const float4*>(rec), featp, Cpad, C, idx_sorted, tile_range, bg, W, H,
-                          final_T, ncontrib, dL_dimage, grec, gfeat, views, touch);
+                          final_T, ncontrib, dL_dimage, grec, gfeat, views);
 }
 
 }  // extern "C"

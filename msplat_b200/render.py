@@ -48,9 +48,6 @@ _tls = threading.local()
 # views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
 VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
 M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
-# forward blend leaves a byte per list entry (which warps blended it) for the backward blend; MSB_TOUCH=0 makes the
-# backward pass repeat the footprint test instead (A/B switch, same results)
-USE_TOUCH = os.environ.get("MSB_TOUCH", "1") != "0"
 
 
 @contextmanager
@@ -284,7 +281,7 @@ class _RenderSHViews(torch.autograd.Function):
             two_stream = side is not None and len(chunks) > 1
             if two_stream:
                 side.wait_stream(main)  # the per-view tensors were produced on `main`
-            ids_all, touch_all, keep = [], [], []
+            ids_all, keep = [], []
             for k, (b0, nb) in enumerate(chunks):
                 M = sum(Ms[b0:b0 + nb])
                 if spec is not None and M <= spec[k][0].numel():
@@ -300,13 +297,10 @@ class _RenderSHViews(torch.autograd.Function):
                               ws2.numel(), _lib.sm_count(dev))
                     if two_stream:
                         main.wait_event(side.record_event())
-                # forward state for the backward blend: which warps of a tile's CTA blended which list entry
-                touch = torch.empty((M,), dtype=torch.uint8, device=dev) if (need_grad and USE_TOUCH) else None
                 _lib.call("blend_forward", _blend_passes_fwd(cpad, C), L.msb_blend_packed_fwd_views, dev, ptr(rec[b0]),
                           ptr(featp[b0]), ptr(ids), ptr(tr[b0 * T:]), bg, C, W, H, nb, ptr(images[b0]),
-                          ptr(final_T[b0]), ptr(ncontrib[b0]), ptr(touch), M)
+                          ptr(final_T[b0]), ptr(ncontrib[b0]))
                 ids_all.append(ids)
-                touch_all.append(touch)
                 keep.append(ws2)  # alive until both streams are joined (allocated on `main`)
             # all side-stream sorts are ordered before the last blend, hence before anything the caller enqueues
             del keep, uv, depth
@@ -321,7 +315,6 @@ class _RenderSHViews(torch.autograd.Function):
         ctx.has_ndc = ndc is not None
         ctx.stats = stats
         ctx.gbuf = (grec, gfeat, cleared)
-        ctx.touch = touch_all
         ctx.gclean = True
         ctx.overlap = overlap  # backward runs on autograd's thread: the caller's serialised() does not reach it
         ctx.save_for_backward(x, s, q, sh, I, E, rec, featp, tiles, tr, final_T, ncontrib, *ids_all)
@@ -369,7 +362,7 @@ class _RenderSHViews(torch.autograd.Function):
                 b0, nb = chunks[k]
                 _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd_views, dev, ptr(rec[b0]),
                           ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[b0 * T:]), bg, Pp, C, W, H, nb, ptr(final_T[b0]),
-                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1, ptr(ctx.touch[k]))
+                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
 
             def pre_bwd(k, lo, hi, accumulate, outs, row_index=None, row_base=0):
                 """fused preprocess backward of chunk k for the Gaussians [lo, hi)"""

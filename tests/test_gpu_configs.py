@@ -10,7 +10,7 @@ import math
 import pytest
 import torch
 
-from test_gpu_parity import DEV, SH_ATOL, compare_grads, grad_close, spread
+from test_gpu_parity import DEV, K_NOISE, SH_ATOL, compare_grads, grad_close, spread
 from test_gpu_render_sh import steps_pipeline
 
 pytestmark = pytest.mark.gpu
@@ -119,13 +119,16 @@ def _config4_compare(ms, ref_msplat, sc, tag, fused=True):
     # the reference's own compute_sh tolerance (SH_ATOL at the tensor's scale, see test_gpu_parity.SH_ATOL)
     nf = [max(f, SH_ATOL * float(r.abs().max())) if n in ("dxyz", "dshs") else f for n, f, r in zip(names, nf, ref)]
     ours = run("steps", lambda L: steps_pipeline(ms, L, sc.intr, sc.extr, sc.W, sc.H, 0.0, False))
+    # 32 channels: dL_dalpha of a pair is a 32-term dot product, accumulated in packed pairs (FFMA2) and in two
+    # 16-channel passes by our kernels, serially by the reference's -- a deterministic difference in summation order
+    # that the run-to-run spread does not contain; measured need: 3.6-4.1 x the spread (dscale), hence 2 K_NOISE here
     for n, a, b, f in zip(names, ours, ref, nf):
-        grad_close(a, b, noise=f, what=f"{tag} steps {n}")
+        grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} steps {n}")
     del ours
     if fused:
         ours = run("fused", lambda L: ms.rasterization_sh(*L, sc.intr, sc.extr, sc.W, sc.H, 0.0))
         for n, a, b, f in zip(names, ours, ref, nf):
-            grad_close(a, b, noise=f, what=f"{tag} fused {n}")
+            grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} fused {n}")
         del ours
     assert out["steps"].shape == (C, sc.H, sc.W)
     scale = max(1.0, float(out["ref"].abs().max()))
