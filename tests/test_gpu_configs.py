@@ -122,13 +122,17 @@ def _config4_compare(ms, ref_msplat, sc, tag, fused=True):
     # 32 channels: dL_dalpha of a pair is a 32-term dot product, accumulated in packed pairs (FFMA2) and in two
     # 16-channel passes by our kernels, serially by the reference's -- a deterministic difference in summation order
     # that the run-to-run spread does not contain; measured need: 3.6-4.1 x the spread (dscale), hence 2 K_NOISE here
+    # clamp_min(sh + 0.5, 0) is discontinuous: of the P x 32 colour values a handful lie within rounding of 0 and
+    # pass the clamp in one library only (the degree-10 bases differ in evaluation order), which switches the 121
+    # dL_dshs entries of that (Gaussian, channel) and the Gaussian's dL_dxyz on or off: all but 1e-5 of the elements
+    frac = 1.0 - 1e-5
     for n, a, b, f in zip(names, ours, ref, nf):
-        grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} steps {n}")
+        grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} steps {n}", min_frac=frac)
     del ours
     if fused:
         ours = run("fused", lambda L: ms.rasterization_sh(*L, sc.intr, sc.extr, sc.W, sc.H, 0.0))
         for n, a, b, f in zip(names, ours, ref, nf):
-            grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} fused {n}")
+            grad_close(a, b, noise=f, k=2 * K_NOISE, what=f"{tag} fused {n}", min_frac=frac)
         del ours
     assert out["steps"].shape == (C, sc.H, sc.W)
     scale = max(1.0, float(out["ref"].abs().max()))

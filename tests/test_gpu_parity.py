@@ -71,10 +71,10 @@ def grad_close(a, b, noise=0.0, what="", rel=REL, k=K_NOISE, min_frac=1.0):
     floor = max(float(noise), ULP_FLOOR * scale)
     d = (a - b).abs()
     need = float(((d - rel * b.abs()) / floor).max())
-    REPORT.append({"what": what, "max_abs_g": scale, "noise_floor": float(noise), "max_abs_err": float(d.max()),
-                   "needed_k": need, "k": k, "rel": rel})
     bad = d > rel * b.abs() + k * floor
     frac_ok = 1.0 - float(bad.double().mean())
+    REPORT.append({"what": what, "max_abs_g": scale, "noise_floor": float(noise), "max_abs_err": float(d.max()),
+                   "needed_k": need, "k": k, "rel": rel, "outside": int(bad.sum()), "of": bad.numel(), "min_frac": min_frac})
     assert frac_ok >= min_frac, f"{what}: {int(bad.sum())}/{bad.numel()} outside {rel:g}|g| + {k:g} x {floor:.3e} " \
                                 f"(max err {float(d.max()):.3e}, scale {scale:.3e}, needs k = {need:.2f})"
 
@@ -579,10 +579,10 @@ def test_alpha_blending_vs_oracle(ms, C, bg):
     # expf (oracle) vs ex2.approx (device): a pair exactly at a threshold may flip for a pixel or two
     flips = int((err.amax(0) > 1e-4).sum())
     assert flips <= 3, f"max abs image error {float(err.max())} on {flips} pixels"
-    # always compared: a flipped pixel changes the gradients of the few Gaussians it blends, so with flips
-    # 99.9 % of the elements must agree, without flips all of them
+    # always compared: a pair within rounding of a threshold blends on one side only (visible in the image only at
+    # high transmittance) and changes the gradients of the few Gaussians of that pixel: 99.9 % of the elements agree
     for name, a, b, f in zip(("dL_duv", "dL_dconic", "dL_dopacity", "dL_dfeature"), ours, ref, nf):
-        grad_close(a, b, noise=f, k=K_ORACLE, what=f"blend/oracle[C={C}] {name}", min_frac=1.0 if flips == 0 else 0.999)
+        grad_close(a, b, noise=f, k=K_ORACLE, what=f"blend/oracle[C={C}] {name}", min_frac=0.999)
 
 
 def test_alpha_blending_reference_test_shape(ms, golden):
@@ -670,8 +670,7 @@ def test_rasterization_fused_equals_steps_and_oracle(ms):
     assert flips <= 5, f"image err {float(err.max())} on {flips} pixels"
     (img_o * g).sum().backward()
     for n, a, o, f in zip(names[:5], A[:5], O[:5], nf):  # always compared (see test_alpha_blending_vs_oracle)
-        grad_close(a.grad, o.grad, noise=f, k=K_ORACLE, what=f"rasterization/oracle d{n}",
-                   min_frac=1.0 if flips == 0 else 0.999)
+        grad_close(a.grad, o.grad, noise=f, k=K_ORACLE, what=f"rasterization/oracle d{n}", min_frac=0.999)
 
 
 def test_rasterization_vs_reference(ms, ref_msplat):

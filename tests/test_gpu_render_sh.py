@@ -237,7 +237,10 @@ def test_render_sh_vs_oracle(ms):
     assert flips <= 5, f"image err {float(err.max())} on {flips} pixels"
     (img_o * g).sum().backward()
     for n, a, o, f in zip(["xyz", "scale", "quat", "opacity", "shs"], ours, O, nf):
-        grad_close(a, o.grad, noise=f, k=K_ORACLE, what=f"render_sh/oracle d{n}", min_frac=1.0 if flips == 0 else 0.999)
+        # expf (oracle) vs ex2.approx (device): a pair within rounding of the 1/255 threshold blends on one side only;
+        # at low transmittance that stays below the image bar but changes the gradients of the Gaussians of that
+        # pixel, so the comparison is on the elements both sides agree on: at least 99.9 %
+        grad_close(a, o.grad, noise=f, k=K_ORACLE, what=f"render_sh/oracle d{n}", min_frac=0.999)
 
 
 def test_render_sh_vs_reference_steps(ms, ref_msplat):
