@@ -232,13 +232,14 @@ int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const 
  * msb_grad_row_index: after the masks were summed over the ranks: incl [P] = inclusive count of
  *   mask > 0, row_index [P] = incl - 1 where mask > 0 else -1; the count goes to *total_host (PINNED,
  *   asynchronous); ws = msb_sort_scan_workspace_bytes(P).
- * msb_grad_expand_rows: dense [P,row_floats] <- compact[row_index[i] - row_base], zeros where < 0. */
+ * msb_grad_expand_rows: dense [P,row_floats] <- compact[row_index[i] - row_base], zeros where < 0
+ *   (accumulate != 0: the compact rows are added to dense, other rows untouched). */
 int msb_grad_live_mask(const float* gfeat, int P, int views, long long vstride, int Cpad, int32_t* mask,
                        void* stream);
 int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_index, long long* total_host,
                        void* ws, size_t ws_bytes, void* stream);
 int msb_grad_expand_rows(const float* compact, const int32_t* row_index, int row_base, int P, int row_floats,
-                         float* dense, void* stream);
+                         float* dense, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,7 @@ def _declare(lib):
         # view-batch data parallelism
         "msb_grad_live_mask": (I, [P, I, I, LL, I, P, V]),
         "msb_grad_row_index": (I, [P, I, P, P, P, P, SZ, V]),
-        "msb_grad_expand_rows": (I, [P, P, I, I, I, P, V]),
+        "msb_grad_expand_rows": (I, [P, P, I, I, I, P, I, V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly

@@ -653,8 +653,11 @@ __global__ void __launch_bounds__(256) grad_live_mask_kernel(int P, int views, l
     mask[i] = live ? 1 : 0;
 }
 
-// dense[i, :] = row_index[i] >= 0 ? compact[row_index[i] - row_base, :] : 0, rows of `units` elements of T
-template <typename T>
+// dense[i, :] (+)= row_index[i] >= 0 ? compact[row_index[i] - row_base, :] : 0, rows of `units` elements of T
+// (ACC: added to dense, rows without a compact row are left alone)
+__device__ __forceinline__ float add_elem(float a, float b) { return a + b; }
+__device__ __forceinline__ float4 add_elem(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+template <typename T, bool ACC>
 __global__ void __launch_bounds__(256) grad_expand_rows_kernel(long long total, int units, int row_base,
                                                                const int* __restrict__ row_index,
                                                                const T* __restrict__ compact, T* __restrict__ dense) {
@@ -663,10 +666,14 @@ __global__ void __launch_bounds__(256) grad_expand_rows_kernel(long long total, 
     const long long i = e / units;
     const int j = (int)(e - i * units);
     const int r = row_index[i];
-    T v;
-    memset(&v, 0, sizeof(T));
-    if (r >= 0) v = compact[(long long)(r - row_base) * units + j];
-    dense[e] = v;
+    if (ACC) {
+        if (r >= 0) dense[e] = add_elem(dense[e], compact[(long long)(r - row_base) * units + j]);
+    } else {
+        T v;
+        memset(&v, 0, sizeof(T));
+        if (r >= 0) v = compact[(long long)(r - row_base) * units + j];
+        dense[e] = v;
+    }
 }
 
 static size_t rp_smem_fwd(int deg, int Cpad) {
@@ -885,21 +892,29 @@ int msb_grad_live_mask(const float* gfeat, int P, int views, long long vstride, 
     return check_launch("grad_live_mask");
 }
 
-// dense [P, row_floats] <- compact rows (row_index[i] - row_base), zeros where row_index[i] < 0.
+// dense [P, row_floats] <- compact rows (row_index[i] - row_base), zeros where row_index[i] < 0;
+// accumulate != 0: the compact rows are added to dense instead.
 int msb_grad_expand_rows(const float* compact, const int32_t* row_index, int row_base, int P, int row_floats,
-                         float* dense, void* stream) {
+                         float* dense, int accumulate, void* stream) {
     if (P == 0 || row_floats == 0) return MSB_OK;
     if (P < 0 || row_floats < 0 || !row_index || !dense) return set_error(MSB_ERR_ARG, "grad_expand_rows: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if ((row_floats & 3) == 0 && rp_al16(compact) && rp_al16(dense)) {
         const long long total = (long long)P * (row_floats / 4);
-        grad_expand_rows_kernel<float4><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            total, row_floats / 4, row_base, row_index, reinterpret_cast<const float4*>(compact),
-            reinterpret_cast<float4*>(dense));
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        const float4* c4 = reinterpret_cast<const float4*>(compact);
+        float4* d4 = reinterpret_cast<float4*>(dense);
+        if (accumulate)
+            grad_expand_rows_kernel<float4, true><<<grid, 256, 0, st>>>(total, row_floats / 4, row_base, row_index, c4, d4);
+        else
+            grad_expand_rows_kernel<float4, false><<<grid, 256, 0, st>>>(total, row_floats / 4, row_base, row_index, c4, d4);
     } else {
         const long long total = (long long)P * row_floats;
-        grad_expand_rows_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, row_floats, row_base,
-                                                                                       row_index, compact, dense);
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (accumulate)
+            grad_expand_rows_kernel<float, true><<<grid, 256, 0, st>>>(total, row_floats, row_base, row_index, compact, dense);
+        else
+            grad_expand_rows_kernel<float, false><<<grid, 256, 0, st>>>(total, row_floats, row_base, row_index, compact, dense);
     }
     return check_launch("grad_expand_rows");
 }

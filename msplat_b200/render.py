@@ -45,6 +45,9 @@ __all__ = ["rasterization_sh", "rasterization_sh_views", "serialised"]
 OVERLAP = True
 _tls = threading.local()
 
+# data-parallel backward: all-reduce of the first views' gradients under the backward blend of the last ones
+# (MSB_DP_SPLIT=0: one exchange after all blends; A/B switch)
+DP_SPLIT = os.environ.get("MSB_DP_SPLIT", "1") != "0"
 # views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
 VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
 M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
@@ -358,22 +361,25 @@ class _RenderSHViews(torch.autograd.Function):
                 main.wait_event(cleared)
             ctx.gclean = False
 
-            def blend_bwd(k):
+            def blend_bwd(k, v0=None, nv=None):
+                """backward blend of the views [v0, v0 + nv) of chunk k (default: the whole chunk); ids, virtual
+                Gaussian ids and tile-range positions are those of the chunk's sort, so rec / featp / grec / gfeat
+                are passed at the chunk's first view and only the per-view arrays are offset"""
                 b0, nb = chunks[k]
+                v0, nv = (b0, nb) if v0 is None else (v0, nv)
                 _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd_views, dev, ptr(rec[b0]),
-                          ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[b0 * T:]), bg, Pp, C, W, H, nb, ptr(final_T[b0]),
-                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
+                          ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[v0 * T:]), bg, Pp, C, W, H, nv, ptr(final_T[v0]),
+                          ptr(ncontrib[v0]), ptr(g[v0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
 
-            def pre_bwd(k, lo, hi, accumulate, outs, row_index=None, row_base=0):
-                """fused preprocess backward of chunk k for the Gaussians [lo, hi)"""
-                b0, nb = chunks[k]
+            def pre_bwd(v0, nv, lo, hi, accumulate, outs, row_index=None, row_base=0):
+                """fused preprocess backward of the views [v0, v0 + nv) for the Gaussians [lo, hi)"""
                 dxyz, dscale, dquat, dop, dshs = outs
                 _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd_views, dev, ptr(x[lo:hi]),
-                          ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[b0]), ptr(E[b0]), es,
-                          ptr(tiles[b0, lo:]), ptr(grec[b0, lo:]), ptr(gfeat[b0, lo:]),
-                          None if row_index is None else ptr(row_index[lo:hi]), row_base, hi - lo, nb, Pp, Cs, D,
+                          ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[v0]), ptr(E[v0]), es,
+                          ptr(tiles[v0, lo:]), ptr(grec[v0, lo:]), ptr(gfeat[v0, lo:]),
+                          None if row_index is None else ptr(row_index[lo:hi]), row_base, hi - lo, nv, Pp, Cs, D,
                           int(with_depth), sh_bias, int(clamp), int(accumulate), ptr(dxyz), ptr(dscale), ptr(dquat),
-                          ptr(dop), ptr(dshs), ptr(dintr[b0]) if need_i else None, ptr(dextr[b0]) if need_e else None)
+                          ptr(dop), ptr(dshs), ptr(dintr[v0]) if need_i else None, ptr(dextr[v0]) if need_e else None)
 
             if group is None:
                 dxyz = torch.empty((P, 3), dtype=f32, device=dev)
@@ -385,12 +391,12 @@ class _RenderSHViews(torch.autograd.Function):
                 side = _side_stream(dev) if (ctx.overlap and len(chunks) > 1) else None
                 if side is not None:
                     side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
-                for k in range(len(chunks)):
+                for k, (b0, nb) in enumerate(chunks):
                     blend_bwd(k)
                     with torch.cuda.stream(side if side is not None else main):
                         if side is not None:
                             side.wait_event(main.record_event())
-                        pre_bwd(k, 0, P, k > 0, outs)
+                        pre_bwd(b0, nb, 0, P, k > 0, outs)
                 if side is not None:
                     main.wait_stream(side)
             else:
@@ -409,21 +415,62 @@ class _RenderSHViews(torch.autograd.Function):
 
 def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
     """View-batch data parallelism: every rank renders its own views; the per-Gaussian gradients are summed
-    over the ranks.  Only rows that some rank touched are sent (see rasterization_sh_views)."""
+    over the ranks.  The rank's views are split in two parts:
+
+      head  (all but the last ~quarter of the views): backward blend, then -- on the side stream, under the
+            backward blend of the tail, which is issue-bound and leaves HBM and NVLink idle -- the fused
+            preprocess backward into one dense flat buffer and its all-reduce (NCCL);
+      tail  (the last views): backward blend, then only the rows that some rank touched in ITS tail travel:
+            the ranks sum a per-Gaussian "received a colour gradient" mask, the preprocess backward writes
+            its dL_dshs rows compacted to the union, one flat all-reduce per slab of Gaussians carries the 11
+            dense geometry floats plus the compact rows, and the result is added into the head's buffer.
+
+    The all-reduce is linear, so sum_ranks(head + tail) = AR(head) + AR(tail); what stays exposed is the tail's
+    (smaller, sparser) exchange."""
     B, P, Pp, Cs, D, C, cpad = ctx.cfg[:7]
     chunks = ctx.chunks
     L = _lib.lib()
     f32, i32 = torch.float32, torch.int32
     main = torch.cuda.current_stream(dev)
-    for k in range(len(chunks)):
-        blend_bwd(k)
-    # 1. which Gaussians received a colour gradient on this rank -> summed over the ranks (> 0 = union)
+    F = Cs * D
+    P4 = (P + 3) // 4 * 4
+    ntail = max(1, B // 4) if (B >= 2 and ctx.overlap and DP_SPLIT) else B
+    nhead = B - ntail
+    # dense flat buffer of the result: [dxyz | dscale | dquat | dopacity | dshs]; the outputs are views of it
+    flat = torch.empty((11 * P4 + P * F,), dtype=f32, device=dev)
+    out_views = (flat[0:3 * P].view(P, 3), flat[3 * P4:3 * P4 + 3 * P].view(P, 3), flat[6 * P4:6 * P4 + 4 * P].view(P, 4),
+                 flat[10 * P4:10 * P4 + P], flat[11 * P4:].view(P, Cs, D))
+    if P4 != P:
+        flat[:11 * P4].zero_()  # the few padding floats are reduced too
+
+    def pieces(lo_v, hi_v):
+        """(chunk, first view, views) pieces covering the views [lo_v, hi_v)"""
+        out = []
+        for k, (b0, nb) in enumerate(chunks):
+            a, b = max(b0, lo_v), min(b0 + nb, hi_v)
+            if a < b:
+                out.append((k, a, b - a))
+        return out
+
+    work_head = None
+    if nhead > 0:
+        for k, v0, nv in pieces(0, nhead):
+            blend_bwd(k, v0, nv)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for j, (k, v0, nv) in enumerate(pieces(0, nhead)):
+                pre_bwd(v0, nv, 0, P, j > 0, out_views)
+            work_head = _reduce(group, flat, async_op=True)  # NCCL's stream waits for `side`
+    for k, v0, nv in pieces(nhead, B):
+        blend_bwd(k, v0, nv)
+    # tail 1. which Gaussians received a colour gradient in the tail views -> summed over the ranks (> 0 = union)
     mask = torch.empty((P,), dtype=i32, device=dev)
-    _lib.call("grad_live_mask", 1, L.msb_grad_live_mask, dev, ptr(gfeat), P, B, Pp, cpad, ptr(mask))
+    _lib.call("grad_live_mask", 1, L.msb_grad_live_mask, dev, ptr(gfeat[nhead]), P, ntail, Pp, cpad, ptr(mask))
     w = _reduce(group, mask)
     if w is not None and hasattr(w, "wait"):
         w.wait()
-    # 2. compact row of every Gaussian of the union; U and the slab boundaries go to the host
+    # tail 2. compact row of every Gaussian of the union; U and the slab boundaries go to the host
     nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
     step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
     bounds = [(lo, min(P, lo + step)) for lo in range(0, P, step)]
@@ -433,46 +480,48 @@ def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
     total = _lib.pinned_i64(dev, len(bounds) + 1)
     _lib.call("grad_row_index", 4, L.msb_grad_row_index, dev, ptr(mask), P, ptr(incl), ptr(row_index), ptr(total),
               ptr(ws), ws.numel())
-    ends = incl[torch.tensor([hi - 1 for _, hi in bounds], device=dev)].to(torch.int64)
+    ends = torch.stack([incl[hi - 1] for _, hi in bounds]).to(torch.int64)
     total[1:1 + len(bounds)].copy_(ends, non_blocking=True)
     main.record_event().synchronize()
     cum = [0] + [int(total[1 + k]) for k in range(len(bounds))]
-    # 3. per slab: one flat buffer [dxyz | dscale | dquat | dopacity | compact dL_dshs rows], one all-reduce
-    F = Cs * D
+    # tail 3. per slab: one flat buffer [dxyz | dscale | dquat | dopacity | compact dL_dshs rows], one all-reduce
     works, slabs = [], []
-    for k, (lo, hi) in enumerate(bounds):
-        n, u = hi - lo, cum[k + 1] - cum[k]
+    tail = pieces(nhead, B)
+    for kk, (lo, hi) in enumerate(bounds):
+        n, u = hi - lo, cum[kk + 1] - cum[kk]
         n4 = (n + 3) // 4 * 4
-        flat = torch.empty((11 * n4 + u * F,), dtype=f32, device=dev)
+        fl = torch.empty((11 * n4 + u * F,), dtype=f32, device=dev)
         # (a slab without a single live Gaussian still needs a valid dL_dshs pointer: no row is ever written)
-        rows = flat[11 * n4:].view(u, F) if u > 0 else torch.empty((1, F), dtype=f32, device=dev)
-        outs = (flat[0:3 * n].view(n, 3), flat[3 * n4:3 * n4 + 3 * n].view(n, 3),
-                flat[6 * n4:6 * n4 + 4 * n].view(n, 4), flat[10 * n4:10 * n4 + n], rows)
+        rows = fl[11 * n4:].view(u, F) if u > 0 else torch.empty((1, F), dtype=f32, device=dev)
+        outs = (fl[0:3 * n].view(n, 3), fl[3 * n4:3 * n4 + 3 * n].view(n, 3), fl[6 * n4:6 * n4 + 4 * n].view(n, 4),
+                fl[10 * n4:10 * n4 + n], rows)
         if n4 != n:
-            flat[:11 * n4].zero_()  # the few padding floats are reduced too
-        for c in range(len(chunks)):
-            pre_bwd(c, lo, hi, c > 0, outs, row_index, cum[k])
-        works.append(_reduce(group, flat, async_op=True))
+            fl[:11 * n4].zero_()
+        for j, (k, v0, nv) in enumerate(tail):
+            pre_bwd(v0, nv, lo, hi, j > 0, outs, row_index, cum[kk])
+        works.append(_reduce(group, fl, async_op=True))
         slabs.append((lo, hi, outs))
-    # 4. wait, then expand the compact rows back to [P, Cs, D]
-    dxyz = torch.empty((P, 3), dtype=f32, device=dev)
-    dscale = torch.empty((P, 3), dtype=f32, device=dev)
-    dquat = torch.empty((P, 4), dtype=f32, device=dev)
-    dop = torch.empty((P,), dtype=f32, device=dev)
-    dshs = torch.empty_like(sh)
-    for k, (lo, hi, outs) in enumerate(slabs):
-        if works[k] is not None and hasattr(works[k], "wait"):
-            works[k].wait()
-        dxyz[lo:hi].copy_(outs[0])
-        dscale[lo:hi].copy_(outs[1])
-        dquat[lo:hi].copy_(outs[2])
-        dop[lo:hi].copy_(outs[3])
-        _lib.call("grad_expand_rows", 1, L.msb_grad_expand_rows, dev, ptr(outs[4]), ptr(row_index[lo:hi]), cum[k],
-                  hi - lo, F, ptr(dshs[lo:hi]))
+    # 4. wait; tail + head -> the dense result
+    if work_head is not None and hasattr(work_head, "wait"):
+        work_head.wait()
+    if nhead > 0:
+        main.wait_stream(_side_stream(dev))
+    for kk, (lo, hi, outs) in enumerate(slabs):
+        if works[kk] is not None and hasattr(works[kk], "wait"):
+            works[kk].wait()
+        if nhead > 0:
+            for dst, src in zip(out_views[:4], outs[:4]):
+                dst[lo:hi].add_(src)
+        else:
+            for dst, src in zip(out_views[:4], outs[:4]):
+                dst[lo:hi].copy_(src)
+        _lib.call("grad_expand_rows", 1, L.msb_grad_expand_rows, dev, ptr(outs[4]), ptr(row_index[lo:hi]), cum[kk],
+                  hi - lo, F, ptr(out_views[4][lo:hi]), 1 if nhead > 0 else 0)
     if ctx.stats is not None:
         ctx.stats["allreduce_floats"] = (cum[-1] - cum[0]) * F + 11 * P
         ctx.stats["allreduce_dense_floats"] = P * (11 + F)
-    return dxyz, dscale, dquat, dop, dshs
+        ctx.stats["allreduce_head_floats"] = int(flat.numel()) if nhead > 0 else 0
+    return out_views
 
 
 def _blend_passes_fwd(cpad: int, C: int) -> int:
