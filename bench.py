@@ -245,15 +245,13 @@ def run_gpu(args, api, impl):
         flat.all_reduce()
         return total
 
-    dp_stats = {} if world > 1 else None
-
     def step_fused(intrs, extrs, cents, G_):
         """one autograd Function over the view batch; gradients come back already summed"""
         for p_ in params:
             p_.grad = None
         images = api.rasterization_sh_views(*params, intrs, extrs, W, H, 0.0, with_depth=True,
                                             grad_sync=(world > 1),  # grads come back summed over the ranks
-                                            grad_chunks=args.grad_chunks, view_chunk=args.view_chunk, stats=dp_stats)
+                                            grad_chunks=args.grad_chunks, view_chunk=args.view_chunk)
         loss = (images * resolve(G_)).sum()
         loss.backward()
         return loss.detach()
@@ -365,10 +363,7 @@ def run_gpu(args, api, impl):
     api_note = ("msplat_b200.rasterization_sh_views (fused view-batch Function: one preprocess / sort / blend launch "
                 "per view batch)" if fused else
                 "steps API: project_point/compute_sh/compute_cov3d/ewa_project/sort_gaussian/alpha_blending per view")
-    sync_note = ""
-    if world > 1:
-        sync_note = (", per-Gaussian grads summed over the ranks once per step (NCCL all-reduce of the rows some rank "
-                     "touched)" if fused else ", one NCCL sum all-reduce of the flat grads per step")
+    sync_note = ", one NCCL sum all-reduce of the per-Gaussian grads per step" if world > 1 else ""
     out = {
         "metric": METRIC5 if cfg5 else METRIC, "value": value, "unit": "renders/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -391,11 +386,10 @@ def run_gpu(args, api, impl):
         out["serial_ms_per_step"] = serial_ms  # same step with the two-stream overlap switched off (stage timings)
         out["stage_ms_two_stream"] = overlapped  # per-call durations while overlapping with the other stream
         out.update(stage_report(timing, args, api, params, cams_host, G, clocks, V, world))
-        if dp_stats:
-            sent, dense = dp_stats.get("allreduce_floats"), dp_stats.get("allreduce_dense_floats")
-            if sent and dense:
-                out["grad_exchange"] = {"bytes_per_step": 4 * sent, "dense_bytes": 4 * dense,
-                                        "fraction_of_dense": round(sent / dense, 4)}
+        if world > 1:
+            out["grad_exchange"] = {"bytes_per_step": 4 * P * (11 + 3 * (SH_DEG + 1) ** 2),
+                                    "note": "dense FP32 sum all-reduce of [P, 3+3+4+1+Cs*D], one coalesced NCCL call per "
+                                            "slab of Gaussians, overlapped with the preprocess backward of the next slab"}
         if fused and not args.no_steps_api and not cfg5:
             s_ms, s_val, s_e2e, _, _, _ = measure(step_steps)
             out["steps_api"] = {"value": s_val, "e2e": s_e2e, "ms_per_step": s_ms, "unit": "renders/s",
@@ -735,7 +729,7 @@ def main():
     ap.add_argument("--api", default="fused", choices=["fused", "steps"],
                     help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
     ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
-    ap.add_argument("--grad-chunks", type=int, default=2,
+    ap.add_argument("--grad-chunks", type=int, default=3,
                     help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels")
     ap.add_argument("--view-chunk", type=int, default=0, help="views per batched launch (0 = all views of the rank)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 5],

@@ -209,9 +209,7 @@ int msb_blend_packed_count(const float* rec, const int32_t* idx_sorted, const in
  * rec [views,vstride,8], featp [views,vstride,Cpad], uv [views,vstride,2], depth / radius / tiles
  * [views,vstride], grec / gfeat like rec / featp; total_dev [views] int64 (optional) = M per view.
  * backward: per-Gaussian pointers may be offset to a slab of P Gaussians (tiles / grec / gfeat to the same
- * row of view 0).  row_index [P] (optional): dL_dshs row of Gaussian i is row_index[i] - row_base of a compact
- * [rows,Cs,D] buffer, negative = no row.  dL_dintr [views,4] / dL_dextr [views,estride] optional,
- * accumulated into; dL_dextr includes the view direction's dependence on the camera centre -R^T t. */
+ * row of view 0).  dL_dintr [views,4] / dL_dextr [views,estride] optional, accumulated into; dL_dextr includes the view direction's dependence on the camera centre -R^T t. */
 int msb_render_preprocess_fwd_views(const float* xyz, const float* scale, const float* quat, const float* opacity,
                                     const float* shs, const float* intr, const float* extr, int estride, int P,
                                     int views, long long vstride, int Cs, int D, int with_depth, int W, int H,
@@ -220,26 +218,11 @@ int msb_render_preprocess_fwd_views(const float* xyz, const float* scale, const 
                                     void* stream);
 int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const float* quat, const float* shs,
                                     const float* intr, const float* extr, int estride, const int32_t* tiles,
-                                    const float* grec, const float* gfeat, const int32_t* row_index, int row_base,
-                                    int P, int views, long long vstride, int Cs, int D, int with_depth,
+                                    const float* grec, const float* gfeat, int P, int views, long long vstride,
+                                    int Cs, int D, int with_depth,
                                     float sh_bias, int clamp, int accumulate, float* dL_dxyz, float* dL_dscale,
                                     float* dL_dquat, float* dL_dopacity, float* dL_dshs, float* dL_dintr,
                                     float* dL_dextr, void* stream);
-
-/* ---- view-batch data parallelism: exchange only the dL_dshs rows some rank touched ------------------
- * (no reference counterpart: the reference has no distributed code)
- * msb_grad_live_mask: mask [P] int32 = 1 where any view's gfeat [views,vstride,Cpad] row is non-zero.
- * msb_grad_row_index: after the masks were summed over the ranks: incl [P] = inclusive count of
- *   mask > 0, row_index [P] = incl - 1 where mask > 0 else -1; the count goes to *total_host (PINNED,
- *   asynchronous); ws = msb_sort_scan_workspace_bytes(P).
- * msb_grad_expand_rows: dense [P,row_floats] <- compact[row_index[i] - row_base], zeros where < 0
- *   (accumulate != 0: the compact rows are added to dense, other rows untouched). */
-int msb_grad_live_mask(const float* gfeat, int P, int views, long long vstride, int Cpad, int32_t* mask,
-                       void* stream);
-int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_index, long long* total_host,
-                       void* ws, size_t ws_bytes, void* stream);
-int msb_grad_expand_rows(const float* compact, const int32_t* row_index, int row_base, int P, int row_floats,
-                         float* dense, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,11 +69,7 @@ def _declare(lib):
         "msb_blend_packed_bwd_views": (I, [P, P, P, P, F, I, I, I, I, I, P, P, P, P, P, I, V]),
         "msb_blend_packed_count": (I, [P, P, P, I, I, I, P, V]),
         "msb_render_preprocess_fwd_views": (I, [P] * 7 + [I, I, I, LL, I, I, I, I, I, F, F, F, I] + [P] * 7 + [V]),
-        "msb_render_preprocess_bwd_views": (I, [P] * 6 + [I] + [P] * 4 + [I, I, I, LL, I, I, I, F, I, I] + [P] * 7 + [V]),
-        # view-batch data parallelism
-        "msb_grad_live_mask": (I, [P, I, I, LL, I, P, V]),
-        "msb_grad_row_index": (I, [P, I, P, P, P, P, SZ, V]),
-        "msb_grad_expand_rows": (I, [P, P, I, I, I, P, I, V]),
+        "msb_render_preprocess_bwd_views": (I, [P] * 6 + [I] + [P] * 3 + [I, I, LL, I, I, I, F, I, I] + [P] * 7 + [V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly

@@ -289,15 +289,14 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 5 : 2) render_pre_fwd_kernel
 // packed blend gradients of view b + 1 (grec / gfeat [views, vstride, ...]) are prefetched by TMA while
 // view b is processed, the geometry gradients of all views are summed in registers and leave once, and
 // dL_dshs rows are written by view 0 and reduced into (red.global.add.v4 at the L2, where the row still
-// sits) by the later views.  row_index (optional) redirects the dL_dshs row of Gaussian i to the compact
-// row row_index[i] (< 0: no row) -- the data-parallel path all-reduces only the rows some rank touches.
+// sits) by the later views.
 template <int DEG, bool CAM>
 __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel(
     int P, int Cs, int Cpad, int with_depth, int accumulate, int views, long long vstride,
     const float* __restrict__ xyz, const float* __restrict__ scale, const float* __restrict__ quat,
     const float* __restrict__ shs, const float* __restrict__ intr, const float* __restrict__ extr, int estride,
     float sh_bias, int clamp, const int* __restrict__ tiles, const float* __restrict__ grec,
-    const float* __restrict__ gfeat, const int* __restrict__ row_index, int row_base, float* __restrict__ dL_dxyz,
+    const float* __restrict__ gfeat, float* __restrict__ dL_dxyz,
     float* __restrict__ dL_dscale, float* __restrict__ dL_dquat, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dshs, float* __restrict__ dL_dintr, float* __restrict__ dL_dextr) {
     constexpr int D = sh_dim(DEG);
@@ -371,15 +370,6 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     }
 
     const int t = tid;
-    // >= 0: this Gaussian has a dL_dshs row (compact mode: row row_index[i] - row_base of dL_dshs)
-    int ri = -1;
-    if (t < rows) {
-        ri = 0;
-        if (row_index != nullptr) {
-            const int raw = row_index[g0 + t];
-            ri = raw >= 0 ? raw - row_base : -1;
-        }
-    }
     // geometry gradients, summed over the views in registers
     float dx = 0.f, dy = 0.f, dz = 0.f, dop = 0.f;
     float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -407,7 +397,7 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
         bool vis = false, live = false;
         if (t < rows) {
             vis = tiles[v0 + t] > 0;
-            if (vis && ri >= 0) {
+            if (vis) {
                 const float* gf = s_gfeat + (size_t)t * Cpad;
                 for (int k = 0; k < Cs; ++k) live = live || (gf[k] != 0.f);
                 if (live) {
@@ -420,11 +410,10 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
         // write mode (first view of a launch that does not accumulate): every row of dL_dshs must be produced
         // (zeros for untouched Gaussians); otherwise only rows that actually change are touched
         const bool zf_b = zero_fill && !acc_b;
-        const bool listed = (acc_b || zf_b) ? live : (ri >= 0);
+        const bool listed = (acc_b || zf_b) ? live : (t < rows);
         list_append(listed, (unsigned)t | (vis ? 0u : RP_INVISIBLE) | (live ? 0u : RP_DEAD), s_list, &s_cnt);
-        if (ZF && zf_b && ri >= 0 && !live) {
-            const long long rrow = row_index != nullptr ? (long long)ri : g0 + t;  // ri already has row_base removed
-            char* row = reinterpret_cast<char*>(dL_dshs) + (size_t)rrow * row_bytes;
+        if (ZF && zf_b && t < rows && !live) {
+            char* row = reinterpret_cast<char*>(dL_dshs) + (size_t)(g0 + t) * row_bytes;
             for (size_t off = 0; off < row_bytes; off += ZB * sizeof(float))
                 bulk_s2g(row + off, s_zero, (unsigned)min((size_t)(ZB * sizeof(float)), row_bytes - off));
             bulk_commit();
@@ -452,8 +441,6 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
                 }
             }
             const long long row0 = (g0 + gl) * Cs;
-            const long long orow0 =
-                (row_index != nullptr ? (long long)(act ? row_index[g0 + gl] - row_base : 0) : g0 + gl) * Cs;
             for (int c0 = 0; c0 < Cs; c0 += CU) {
                 // fetch CU coefficient rows at once (memory-level parallelism), then consume them
                 float sv[CU][IT * WD];
@@ -480,7 +467,7 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
                 for (int cc2 = 0; cc2 < CU; ++cc2) {
                     const int ch = c0 + cc2;
                     if (ch >= Cs) break;  // uniform across the block
-                    float* op = dL_dshs + (orow0 + ch) * D;
+                    float* op = dL_dshs + (row0 + ch) * D;
                     const float gv = lv ? s_gfeat[(size_t)gl * Cpad + ch] : 0.f;
                     float acc = 0.f;
 #pragma unroll
@@ -633,49 +620,6 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     if ((full && tid == 0) || filled) bulk_wait_read();  // shared memory stays valid until the copy engine has read it
 }
 
-// ------------------------------------------------------------------------------------------------
-// view-batch data parallelism: send only the dL_dshs rows that some rank touched
-// ------------------------------------------------------------------------------------------------
-// mask[i] = 1 if Gaussian i received a feature gradient in any view of the batch (a superset of the rows
-// render_pre_bwd_kernel touches: it tests the first Cs of these Cpad columns), else 0.
-__global__ void __launch_bounds__(256) grad_live_mask_kernel(int P, int views, long long vstride, int Cpad,
-                                                             const float* __restrict__ gfeat, int* __restrict__ mask) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    bool live = false;
-    for (int b = 0; b < views; ++b) {
-        const float4* row = reinterpret_cast<const float4*>(gfeat + ((long long)b * vstride + i) * Cpad);
-        for (int k = 0; k < Cpad / 4; ++k) {
-            const float4 v = ldg_stream4(row + k);
-            live = live || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
-        }
-    }
-    mask[i] = live ? 1 : 0;
-}
-
-// dense[i, :] (+)= row_index[i] >= 0 ? compact[row_index[i] - row_base, :] : 0, rows of `units` elements of T
-// (ACC: added to dense, rows without a compact row are left alone)
-__device__ __forceinline__ float add_elem(float a, float b) { return a + b; }
-__device__ __forceinline__ float4 add_elem(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-template <typename T, bool ACC>
-__global__ void __launch_bounds__(256) grad_expand_rows_kernel(long long total, int units, int row_base,
-                                                               const int* __restrict__ row_index,
-                                                               const T* __restrict__ compact, T* __restrict__ dense) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const long long i = e / units;
-    const int j = (int)(e - i * units);
-    const int r = row_index[i];
-    if (ACC) {
-        if (r >= 0) dense[e] = add_elem(dense[e], compact[(long long)(r - row_base) * units + j]);
-    } else {
-        T v;
-        memset(&v, 0, sizeof(T));
-        if (r >= 0) v = compact[(long long)(r - row_base) * units + j];
-        dense[e] = v;
-    }
-}
-
 static size_t rp_smem_fwd(int deg, int Cpad) {
     const int G = rp_gpb(deg);
     return ((size_t)21 * G + rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
@@ -724,8 +668,6 @@ struct RpBwdArgs {
     int clamp;
     const int* tiles;
     const float *grec, *gfeat;
-    const int* row_index;
-    int row_base;
     float *dxyz, *dscale, *dquat, *dopacity, *dshs, *dintr, *dextr;
 };
 
@@ -742,8 +684,8 @@ static int rp_launch_bwd(const RpBwdArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)(((long long)a.P + G - 1) / G);
     render_pre_bwd_kernel<DEG, CAM><<<grid, RP_NT, smem, st>>>(
         a.P, a.Cs, a.Cpad, a.with_depth, a.accumulate, a.views, a.vstride, a.xyz, a.scale, a.quat, a.shs, a.intr,
-        a.extr, a.estride, a.sh_bias, a.clamp, a.tiles, a.grec, a.gfeat, a.row_index, a.row_base, a.dxyz, a.dscale,
-        a.dquat, a.dopacity, a.dshs, a.dintr, a.dextr);
+        a.extr, a.estride, a.sh_bias, a.clamp, a.tiles, a.grec, a.gfeat, a.dxyz, a.dscale, a.dquat, a.dopacity, a.dshs,
+        a.dintr, a.dextr);
     return check_launch("render_preprocess_bwd");
 }
 
@@ -833,13 +775,10 @@ int msb_render_preprocess_fwd(const float* xyz, const float* scale, const float*
 // counts and the packed gradients written by msb_blend_packed_bwd_views; per-Gaussian pointers (xyz ...
 // dL_dshs, tiles, grec, gfeat) may be offset to a slab of P Gaussians.  The gradients are summed over the
 // views.  accumulate != 0: added to the outputs; otherwise every output element is written.
-// row_index [P] (optional, int32): dL_dshs row of Gaussian i is row_index[i] - row_base of a compact
-// [rows, Cs, D] buffer, negative row_index = the Gaussian has no row (and must not have a colour gradient).
 // dL_dintr [views,4] / dL_dextr [views,estride] may be NULL; otherwise they are accumulated into.
 int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const float* quat, const float* shs,
                                     const float* intr, const float* extr, int estride, const int32_t* tiles,
-                                    const float* grec, const float* gfeat, const int32_t* row_index, int row_base,
-                                    int P, int views, long long vstride, int Cs, int D, int with_depth, float sh_bias, int clamp,
+                                    const float* grec, const float* gfeat, int P, int views, long long vstride, int Cs, int D, int with_depth, float sh_bias, int clamp,
                                     int accumulate, float* dL_dxyz, float* dL_dscale, float* dL_dquat,
                                     float* dL_dopacity, float* dL_dshs, float* dL_dintr, float* dL_dextr,
                                     void* stream) {
@@ -856,7 +795,7 @@ int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const 
         return set_error(MSB_ERR_ARG, "render_preprocess_bwd: 16-byte alignment");
     RpBwdArgs a{P, Cs, msb_blend_cpad(Cs + (with_depth ? 1 : 0)), with_depth ? 1 : 0, accumulate ? 1 : 0, views,
                 vstride, xyz, scale, quat, shs, intr, extr, estride, sh_bias, clamp ? 1 : 0, tiles, grec, gfeat,
-                row_index, row_base, dL_dxyz, dL_dscale, dL_dquat, dL_dopacity, dL_dshs, dL_dintr, dL_dextr};
+                dL_dxyz, dL_dscale, dL_dquat, dL_dopacity, dL_dshs, dL_dintr, dL_dextr};
     cudaStream_t st = (cudaStream_t)stream;
     const bool camg = dL_dintr || dL_dextr;
     switch (deg) {
@@ -876,47 +815,9 @@ int msb_render_preprocess_bwd(const float* xyz, const float* scale, const float*
                               const float* gfeat, int P, int Cs, int D, int with_depth, float sh_bias, int clamp,
                               int accumulate, float* dL_dxyz, float* dL_dscale, float* dL_dquat, float* dL_dopacity,
                               float* dL_dshs, float* dL_dintr, float* dL_dextr, void* stream) {
-    return msb_render_preprocess_bwd_views(xyz, scale, quat, shs, intr, extr, 12, tiles, grec, gfeat, nullptr, 0, P, 1, P,
+    return msb_render_preprocess_bwd_views(xyz, scale, quat, shs, intr, extr, 12, tiles, grec, gfeat, P, 1, P,
                                            Cs, D, with_depth, sh_bias, clamp, accumulate, dL_dxyz, dL_dscale, dL_dquat,
                                            dL_dopacity, dL_dshs, dL_dintr, dL_dextr, stream);
-}
-
-// ---- view-batch data parallelism (msplat_b200/render.py::_backward_data_parallel) ---------------------
-// mask [P] int32 = 1 where any view's gfeat [views,vstride,Cpad] row of the Gaussian is non-zero.
-int msb_grad_live_mask(const float* gfeat, int P, int views, long long vstride, int Cpad, int32_t* mask, void* stream) {
-    if (P == 0) return MSB_OK;
-    if (P < 0 || views <= 0 || Cpad <= 0 || (Cpad & 3) || !gfeat || !mask || !rp_al16(gfeat))
-        return set_error(MSB_ERR_ARG, "grad_live_mask: bad argument");
-    grad_live_mask_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, views, vstride, Cpad, gfeat,
-                                                                                       mask);
-    return check_launch("grad_live_mask");
-}
-
-// dense [P, row_floats] <- compact rows (row_index[i] - row_base), zeros where row_index[i] < 0;
-// accumulate != 0: the compact rows are added to dense instead.
-int msb_grad_expand_rows(const float* compact, const int32_t* row_index, int row_base, int P, int row_floats,
-                         float* dense, int accumulate, void* stream) {
-    if (P == 0 || row_floats == 0) return MSB_OK;
-    if (P < 0 || row_floats < 0 || !row_index || !dense) return set_error(MSB_ERR_ARG, "grad_expand_rows: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    if ((row_floats & 3) == 0 && rp_al16(compact) && rp_al16(dense)) {
-        const long long total = (long long)P * (row_floats / 4);
-        const unsigned grid = (unsigned)((total + 255) / 256);
-        const float4* c4 = reinterpret_cast<const float4*>(compact);
-        float4* d4 = reinterpret_cast<float4*>(dense);
-        if (accumulate)
-            grad_expand_rows_kernel<float4, true><<<grid, 256, 0, st>>>(total, row_floats / 4, row_base, row_index, c4, d4);
-        else
-            grad_expand_rows_kernel<float4, false><<<grid, 256, 0, st>>>(total, row_floats / 4, row_base, row_index, c4, d4);
-    } else {
-        const long long total = (long long)P * row_floats;
-        const unsigned grid = (unsigned)((total + 255) / 256);
-        if (accumulate)
-            grad_expand_rows_kernel<float, true><<<grid, 256, 0, st>>>(total, row_floats, row_base, row_index, compact, dense);
-        else
-            grad_expand_rows_kernel<float, false><<<grid, 256, 0, st>>>(total, row_floats, row_base, row_index, compact, dense);
-    }
-    return check_launch("grad_expand_rows");
 }
 
 }  // extern "C"

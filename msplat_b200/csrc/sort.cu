@@ -82,13 +82,9 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp /*[NTH/32 + 1]
     return res;
 }
 
-// value i of the scanned sequence (BIN: 1 where vals[i] > 0 -- counts instead of sums)
-template <bool BIN = false>
-__device__ __forceinline__ int scan_value(const int* __restrict__ vals, long long i) {
-    return BIN ? (vals[i] > 0 ? 1 : 0) : max(vals[i], 0);
-}
+// value i of the scanned sequence
+__device__ __forceinline__ int scan_value(const int* __restrict__ vals, long long i) { return max(vals[i], 0); }
 
-template <bool BIN = false>
 __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int* __restrict__ vals,
                                                                 long long* __restrict__ bsum) {
     __shared__ long long s_part[SC_NT / 32];
@@ -97,7 +93,7 @@ __global__ void __launch_bounds__(SC_NT) scan_block_sums_kernel(int P, const int
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k * SC_NT + threadIdx.x;
-        if (i < P) acc += scan_value<BIN>(vals, i);
+        if (i < P) acc += scan_value(vals, i);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -147,7 +143,7 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(int nb, long long* __r
 }
 
 // out[i] = (EXCL ? exclusive : inclusive) prefix of the sequence
-template <bool EXCL, bool BIN = false>
+template <bool EXCL>
 __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __restrict__ vals,
                                                            const long long* __restrict__ bsum,
                                                            int* __restrict__ out) {
@@ -158,7 +154,7 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
         const long long i = base + k;
-        v[k] = i < P ? scan_value<BIN>(vals, i) : 0;
+        v[k] = i < P ? scan_value(vals, i) : 0;
         sum += v[k];
     }
     int total;
@@ -174,13 +170,6 @@ __global__ void __launch_bounds__(SC_NT) scan_apply_kernel(int P, const int* __r
             if (i < P) out[i] = run;  // inclusive, like torch.cumsum
         }
     }
-}
-
-// row_index[i] = mask[i] > 0 ? incl[i] - 1 : -1 (incl = inclusive prefix count of mask > 0)
-__global__ void __launch_bounds__(256) row_index_kernel(int P, const int* __restrict__ mask,
-                                                        const int* __restrict__ incl, int* __restrict__ row_index) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) row_index[i] = mask[i] > 0 ? incl[i] - 1 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -889,40 +878,13 @@ int msb_sort_scan(const int32_t* tiles, int P, int32_t* offsets, long long* tota
     const int nb = (P + SC_TILE - 1) / SC_TILE;
     long long* bsum = reinterpret_cast<long long*>(ws);
     long long* total_dev = bsum + nb;
-    scan_block_sums_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
+    scan_block_sums_kernel<<<nb, SC_NT, 0, st>>>(P, tiles, bsum);
     scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
     if (offsets) scan_apply_kernel<false><<<nb, SC_NT, 0, st>>>(P, tiles, bsum, offsets);
     int rc = check_launch("sort_scan");
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return set_error((int)e, "sort_scan: cudaMemcpyAsync failed");
-    return MSB_OK;
-}
-
-// Compact row indices for the data-parallel gradient exchange (msplat_b200/render.py): incl [P] =
-// inclusive count of mask > 0, row_index [P] = incl - 1 where mask > 0 else -1; the count of set entries is
-// copied asynchronously to *total_host (pinned).  ws: msb_sort_scan_workspace_bytes(P).
-int msb_grad_row_index(const int32_t* mask, int P, int32_t* incl, int32_t* row_index, long long* total_host, void* ws,
-                       size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (P < 0 || !total_host) return set_error(MSB_ERR_ARG, "grad_row_index: bad argument");
-    if (P == 0) {
-        *total_host = 0;
-        return MSB_OK;
-    }
-    if (!mask || !incl || !row_index || !ws) return set_error(MSB_ERR_ARG, "grad_row_index: null pointer");
-    if (ws_bytes < msb_sort_scan_workspace_bytes(P)) return set_error(MSB_ERR_WORKSPACE, "grad_row_index: workspace too small");
-    const int nb = (P + SC_TILE - 1) / SC_TILE;
-    long long* bsum = reinterpret_cast<long long*>(ws);
-    long long* total_dev = bsum + nb;
-    scan_block_sums_kernel<true><<<nb, SC_NT, 0, st>>>(P, mask, bsum);
-    scan_spine_kernel<<<1, 1024, 0, st>>>(nb, bsum, total_dev);
-    scan_apply_kernel<false, true><<<nb, SC_NT, 0, st>>>(P, mask, bsum, incl);
-    row_index_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, mask, incl, row_index);
-    int rc = check_launch("grad_row_index");
-    if (rc) return rc;
-    cudaError_t e = cudaMemcpyAsync(total_host, total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return set_error((int)e, "grad_row_index: cudaMemcpyAsync failed");
     return MSB_OK;
 }
 

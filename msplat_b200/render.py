@@ -45,9 +45,9 @@ __all__ = ["rasterization_sh", "rasterization_sh_views", "serialised"]
 OVERLAP = True
 _tls = threading.local()
 
-# data-parallel backward: all-reduce of the first views' gradients under the backward blend of the last ones
-# (MSB_DP_SPLIT=0: one exchange after all blends; A/B switch)
-DP_SPLIT = os.environ.get("MSB_DP_SPLIT", "1") != "0"
+# backward: fused preprocess backward of the first views on the side stream under the backward blend of the last ones
+# (MSB_BWD_SPLIT=0: one backward blend and one preprocess backward launch, back to back; A/B switch)
+BWD_SPLIT = os.environ.get("MSB_BWD_SPLIT", "1") != "0"
 # views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
 VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
 M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
@@ -101,7 +101,7 @@ def rasterization_sh(
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 1, ndc: Tensor = None,
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3, ndc: Tensor = None,
     return_aux: bool = False, view_chunk: int = None, stats: dict = None,
 ):
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
@@ -122,14 +122,12 @@ def rasterization_sh_views(
 
     ``grad_sync`` (view-batch data parallelism): a ``torch.distributed`` process group
     (or ``True`` for the default group).  The backward pass then returns the per-Gaussian gradients
-    already SUMMED over the ranks of that group.  Only the rows some rank touched travel: the ranks
-    sum-reduce a per-Gaussian "received a colour gradient" mask (4 B per Gaussian), the fused
-    preprocess backward writes its dL_dshs rows compacted to the union, and ONE flat all-reduce per slab
-    of Gaussians (``grad_chunks`` slabs; a slab's all-reduce runs under the kernels of the next) carries
-    the 11 dense geometry floats plus the compact rows; the result is expanded back to [P,Cs,D].
-    Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a custom
-    reducer: it is called in place with the int32 mask [P] and with every flat float32 slab (sum
-    semantics) and may return an object with ``.wait()``."""
+    already SUMMED over the ranks of that group: the last preprocess-backward launch is cut into
+    ``grad_chunks`` slabs of Gaussians, and the sum all-reduce of a finished slab (one coalesced NCCL call for
+    its five tensors, NCCL's own stream) runs under the kernels of the following slabs instead of after the
+    whole backward.  Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a
+    custom reducer: it is called with every finished gradient slab (in place, sum semantics) and may return an
+    object with ``.wait()``."""
     if intrs.dim() == 1:
         intrs = intrs[None].expand(extrs.shape[0], 4)
     if ndc is not None and tuple(ndc.shape) != (extrs.shape[0], xyz.shape[0], 2):
@@ -162,12 +160,19 @@ def _resolve_group(grad_sync):
     return group if dist.get_world_size(group) > 1 else None
 
 
-def _reduce(group, t, async_op=False):
-    """sum-reduce `t` in place over the group (or through the custom reducer)"""
+def _reduce_many(group, tensors, dev):
+    """sum-reduce every tensor in place over the group, asynchronously (or through the custom reducer): the
+    tensors of one slab go out as ONE coalesced NCCL group call.  -> list of objects with .wait() (or None)"""
     if callable(group):
-        return group(t)
+        return [group(t) for t in tensors]
     import torch.distributed as dist
-    return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    try:
+        with dist._coalescing_manager(group=group, device=torch.device(dev), async_ops=True) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return [cm]
+    except Exception:  # backends without coalescing support: one call per tensor
+        return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in tensors]
 
 
 def _chunks(B, vc):
@@ -371,36 +376,66 @@ class _RenderSHViews(torch.autograd.Function):
                           ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[v0 * T:]), bg, Pp, C, W, H, nv, ptr(final_T[v0]),
                           ptr(ncontrib[v0]), ptr(g[v0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
 
-            def pre_bwd(v0, nv, lo, hi, accumulate, outs, row_index=None, row_base=0):
+            def pre_bwd(v0, nv, lo, hi, accumulate, outs):
                 """fused preprocess backward of the views [v0, v0 + nv) for the Gaussians [lo, hi)"""
                 dxyz, dscale, dquat, dop, dshs = outs
                 _lib.call("render_preprocess_backward", 1, L.msb_render_preprocess_bwd_views, dev, ptr(x[lo:hi]),
                           ptr(s[lo:hi]), ptr(q[lo:hi]), ptr(sh[lo:hi]), ptr(I[v0]), ptr(E[v0]), es,
-                          ptr(tiles[v0, lo:]), ptr(grec[v0, lo:]), ptr(gfeat[v0, lo:]),
-                          None if row_index is None else ptr(row_index[lo:hi]), row_base, hi - lo, nv, Pp, Cs, D,
-                          int(with_depth), sh_bias, int(clamp), int(accumulate), ptr(dxyz), ptr(dscale), ptr(dquat),
-                          ptr(dop), ptr(dshs), ptr(dintr[v0]) if need_i else None, ptr(dextr[v0]) if need_e else None)
+                          ptr(tiles[v0, lo:]), ptr(grec[v0, lo:]), ptr(gfeat[v0, lo:]), hi - lo, nv, Pp, Cs, D,
+                          int(with_depth), sh_bias, int(clamp), int(accumulate), ptr(dxyz[lo:hi]), ptr(dscale[lo:hi]),
+                          ptr(dquat[lo:hi]), ptr(dop[lo:hi]), ptr(dshs[lo:hi]), ptr(dintr[v0]) if need_i else None,
+                          ptr(dextr[v0]) if need_e else None)
 
-            if group is None:
-                dxyz = torch.empty((P, 3), dtype=f32, device=dev)
-                dscale = torch.empty((P, 3), dtype=f32, device=dev)
-                dquat = torch.empty((P, 4), dtype=f32, device=dev)
-                dop = torch.empty((P,), dtype=f32, device=dev)
-                dshs = torch.empty_like(sh)
-                outs = (dxyz, dscale, dquat, dop, dshs)
-                side = _side_stream(dev) if (ctx.overlap and len(chunks) > 1) else None
-                if side is not None:
-                    side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
+            def pieces(lo_v, hi_v):
+                """(chunk, first view, views) pieces covering the views [lo_v, hi_v)"""
+                out = []
                 for k, (b0, nb) in enumerate(chunks):
-                    blend_bwd(k)
-                    with torch.cuda.stream(side if side is not None else main):
-                        if side is not None:
-                            side.wait_event(main.record_event())
-                        pre_bwd(b0, nb, 0, P, k > 0, outs)
-                if side is not None:
-                    main.wait_stream(side)
+                    a_, b_ = max(b0, lo_v), min(b0 + nb, hi_v)
+                    if a_ < b_:
+                        out.append((k, a_, b_ - a_))
+                return out
+
+            dxyz = torch.empty((P, 3), dtype=f32, device=dev)
+            dscale = torch.empty((P, 3), dtype=f32, device=dev)
+            dquat = torch.empty((P, 4), dtype=f32, device=dev)
+            dop = torch.empty((P,), dtype=f32, device=dev)
+            dshs = torch.empty_like(sh)
+            outs = (dxyz, dscale, dquat, dop, dshs)
+            # Schedule.  The views are split into a head and a tail (the last ~quarter).  The fused preprocess
+            # backward of the head (HBM-bound) runs on the side stream under the backward blend of the tail
+            # (issue-bound); the tail's own preprocess backward then adds into the same sums.  With grad_sync
+            # (view-batch data parallelism, SURVEY 8e) that last launch is cut into slabs of Gaussians and the sum
+            # all-reduce of a finished slab (NCCL, its own stream) runs under the kernels of the next slab.
+            ntail = max(1, B // 4) if (B >= 4 and ctx.overlap and BWD_SPLIT) else B
+            nhead = B - ntail
+            side = _side_stream(dev) if nhead > 0 else None
+            for k, v0, nv in pieces(0, nhead):
+                blend_bwd(k, v0, nv)
+            if side is not None:
+                side.wait_stream(main)  # the head's packed gradients; the outputs were allocated on `main`
+                with torch.cuda.stream(side):
+                    for j, (k, v0, nv) in enumerate(pieces(0, nhead)):
+                        pre_bwd(v0, nv, 0, P, j > 0, outs)
+            for k, v0, nv in pieces(nhead, B):
+                blend_bwd(k, v0, nv)
+            if side is not None:
+                main.wait_stream(side)
+            tail = pieces(nhead, B)
+            if group is None:
+                for j, (k, v0, nv) in enumerate(tail):
+                    pre_bwd(v0, nv, 0, P, nhead > 0 or j > 0, outs)
             else:
-                dxyz, dscale, dquat, dop, dshs = _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev)
+                nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
+                step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
+                works = []
+                for lo in range(0, P, step):
+                    hi = min(P, lo + step)
+                    for j, (k, v0, nv) in enumerate(tail):
+                        pre_bwd(v0, nv, lo, hi, nhead > 0 or j > 0, outs)
+                    works += _reduce_many(group, [t[lo:hi] for t in outs], dev)
+                for w in works:
+                    if w is not None and hasattr(w, "wait"):
+                        w.wait()
             gr = grec[:, :P]
             if ctx.has_ndc:  # screen-space gradient hook: dL_duv of view b is columns 0:2 of its packed record
                 dndc = gr[:, :, :2] * torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev)
@@ -411,117 +446,6 @@ class _RenderSHViews(torch.autograd.Function):
         return (dxyz, dscale, dquat, dop.reshape(op_shape), dshs, dintr,
                 None if dextr is None else dextr.reshape(ctx.shapes[2]), None, None, None, None, None, None, None, None,
                 None, None, dndc, None, None, None)
-
-
-def _backward_data_parallel(ctx, group, blend_bwd, pre_bwd, sh, gfeat, dev):
-    """View-batch data parallelism: every rank renders its own views; the per-Gaussian gradients are summed
-    over the ranks.  The rank's views are split in two parts:
-
-      head  (all but the last ~quarter of the views): backward blend, then -- on the side stream, under the
-            backward blend of the tail, which is issue-bound and leaves HBM and NVLink idle -- the fused
-            preprocess backward into one dense flat buffer and its all-reduce (NCCL);
-      tail  (the last views): backward blend, then only the rows that some rank touched in ITS tail travel:
-            the ranks sum a per-Gaussian "received a colour gradient" mask, the preprocess backward writes
-            its dL_dshs rows compacted to the union, one flat all-reduce per slab of Gaussians carries the 11
-            dense geometry floats plus the compact rows, and the result is added into the head's buffer.
-
-    The all-reduce is linear, so sum_ranks(head + tail) = AR(head) + AR(tail); what stays exposed is the tail's
-    (smaller, sparser) exchange."""
-    B, P, Pp, Cs, D, C, cpad = ctx.cfg[:7]
-    chunks = ctx.chunks
-    L = _lib.lib()
-    f32, i32 = torch.float32, torch.int32
-    main = torch.cuda.current_stream(dev)
-    F = Cs * D
-    P4 = (P + 3) // 4 * 4
-    ntail = max(1, B // 4) if (B >= 2 and ctx.overlap and DP_SPLIT) else B
-    nhead = B - ntail
-    # dense flat buffer of the result: [dxyz | dscale | dquat | dopacity | dshs]; the outputs are views of it
-    flat = torch.empty((11 * P4 + P * F,), dtype=f32, device=dev)
-    out_views = (flat[0:3 * P].view(P, 3), flat[3 * P4:3 * P4 + 3 * P].view(P, 3), flat[6 * P4:6 * P4 + 4 * P].view(P, 4),
-                 flat[10 * P4:10 * P4 + P], flat[11 * P4:].view(P, Cs, D))
-    if P4 != P:
-        flat[:11 * P4].zero_()  # the few padding floats are reduced too
-
-    def pieces(lo_v, hi_v):
-        """(chunk, first view, views) pieces covering the views [lo_v, hi_v)"""
-        out = []
-        for k, (b0, nb) in enumerate(chunks):
-            a, b = max(b0, lo_v), min(b0 + nb, hi_v)
-            if a < b:
-                out.append((k, a, b - a))
-        return out
-
-    work_head = None
-    if nhead > 0:
-        for k, v0, nv in pieces(0, nhead):
-            blend_bwd(k, v0, nv)
-        side = _side_stream(dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            for j, (k, v0, nv) in enumerate(pieces(0, nhead)):
-                pre_bwd(v0, nv, 0, P, j > 0, out_views)
-            work_head = _reduce(group, flat, async_op=True)  # NCCL's stream waits for `side`
-    for k, v0, nv in pieces(nhead, B):
-        blend_bwd(k, v0, nv)
-    # tail 1. which Gaussians received a colour gradient in the tail views -> summed over the ranks (> 0 = union)
-    mask = torch.empty((P,), dtype=i32, device=dev)
-    _lib.call("grad_live_mask", 1, L.msb_grad_live_mask, dev, ptr(gfeat[nhead]), P, ntail, Pp, cpad, ptr(mask))
-    w = _reduce(group, mask)
-    if w is not None and hasattr(w, "wait"):
-        w.wait()
-    # tail 2. compact row of every Gaussian of the union; U and the slab boundaries go to the host
-    nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
-    step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
-    bounds = [(lo, min(P, lo + step)) for lo in range(0, P, step)]
-    incl = torch.empty((P,), dtype=i32, device=dev)
-    row_index = torch.empty((P,), dtype=i32, device=dev)
-    ws = torch.empty((L.msb_sort_scan_workspace_bytes(P),), dtype=torch.uint8, device=dev)
-    total = _lib.pinned_i64(dev, len(bounds) + 1)
-    _lib.call("grad_row_index", 4, L.msb_grad_row_index, dev, ptr(mask), P, ptr(incl), ptr(row_index), ptr(total),
-              ptr(ws), ws.numel())
-    ends = torch.stack([incl[hi - 1] for _, hi in bounds]).to(torch.int64)
-    total[1:1 + len(bounds)].copy_(ends, non_blocking=True)
-    main.record_event().synchronize()
-    cum = [0] + [int(total[1 + k]) for k in range(len(bounds))]
-    # tail 3. per slab: one flat buffer [dxyz | dscale | dquat | dopacity | compact dL_dshs rows], one all-reduce
-    works, slabs = [], []
-    tail = pieces(nhead, B)
-    for kk, (lo, hi) in enumerate(bounds):
-        n, u = hi - lo, cum[kk + 1] - cum[kk]
-        n4 = (n + 3) // 4 * 4
-        fl = torch.empty((11 * n4 + u * F,), dtype=f32, device=dev)
-        # (a slab without a single live Gaussian still needs a valid dL_dshs pointer: no row is ever written)
-        rows = fl[11 * n4:].view(u, F) if u > 0 else torch.empty((1, F), dtype=f32, device=dev)
-        outs = (fl[0:3 * n].view(n, 3), fl[3 * n4:3 * n4 + 3 * n].view(n, 3), fl[6 * n4:6 * n4 + 4 * n].view(n, 4),
-                fl[10 * n4:10 * n4 + n], rows)
-        if n4 != n:
-            fl[:11 * n4].zero_()
-        for j, (k, v0, nv) in enumerate(tail):
-            pre_bwd(v0, nv, lo, hi, j > 0, outs, row_index, cum[kk])
-        works.append(_reduce(group, fl, async_op=True))
-        slabs.append((lo, hi, outs))
-    # 4. wait; tail + head -> the dense result
-    if work_head is not None and hasattr(work_head, "wait"):
-        work_head.wait()
-    if nhead > 0:
-        main.wait_stream(_side_stream(dev))
-    for kk, (lo, hi, outs) in enumerate(slabs):
-        if works[kk] is not None and hasattr(works[kk], "wait"):
-            works[kk].wait()
-        if nhead > 0:
-            for dst, src in zip(out_views[:4], outs[:4]):
-                dst[lo:hi].add_(src)
-        else:
-            for dst, src in zip(out_views[:4], outs[:4]):
-                dst[lo:hi].copy_(src)
-        _lib.call("grad_expand_rows", 1, L.msb_grad_expand_rows, dev, ptr(outs[4]), ptr(row_index[lo:hi]), cum[kk],
-                  hi - lo, F, ptr(out_views[4][lo:hi]), 1 if nhead > 0 else 0)
-    if ctx.stats is not None:
-        ctx.stats["allreduce_floats"] = (cum[-1] - cum[0]) * F + 11 * P
-        ctx.stats["allreduce_dense_floats"] = P * (11 + F)
-        ctx.stats["allreduce_head_floats"] = int(flat.numel()) if nhead > 0 else 0
-    return out_views
 
 
 def _blend_passes_fwd(cpad: int, C: int) -> int:
