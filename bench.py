@@ -259,7 +259,10 @@ def run_gpu(args, api, impl):
     def measure(step, stages=False):
         """-> (ms per step resident, renders/s resident, renders/s e2e, launches, timing)"""
         dev_in = (intr_h.to(dev), extr_h.to(dev), cent_h.to(dev), G)
-        for _ in range(args.warmup):
+        # N > 1: the caching allocator needs a few more steps than a single-GPU run to reach its steady state (blocks
+        # that NCCL's stream still uses cannot be recycled at once; until enough exist every step pays cudaMalloc):
+        # measured at N = 2, 3 warm-up steps leave the first timed steps 30-40 % slow.  Warm-up is untimed.
+        for _ in range(max(args.warmup, 8) if world > 1 else args.warmup):
             step(*dev_in)
         barrier_sync(world)
         if ours:

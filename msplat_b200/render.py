@@ -45,9 +45,6 @@ __all__ = ["rasterization_sh", "rasterization_sh_views", "serialised"]
 OVERLAP = True
 _tls = threading.local()
 
-# backward: fused preprocess backward of the first views on the side stream under the backward blend of the last ones
-# (MSB_BWD_SPLIT=0: one backward blend and one preprocess backward launch, back to back; A/B switch)
-BWD_SPLIT = os.environ.get("MSB_BWD_SPLIT", "1") != "0"
 # views per chunk of a batch (0 = the whole batch in one chunk); MSB_VIEW_CHUNK overrides the default
 VIEW_CHUNK = int(os.environ.get("MSB_VIEW_CHUNK", "0"))
 M_MAX = 2 ** 31 - 1  # int32 positions in idx_sorted, the reference's bound (msplat/sort_gaussian.py:42)
@@ -366,15 +363,12 @@ class _RenderSHViews(torch.autograd.Function):
                 main.wait_event(cleared)
             ctx.gclean = False
 
-            def blend_bwd(k, v0=None, nv=None):
-                """backward blend of the views [v0, v0 + nv) of chunk k (default: the whole chunk); ids, virtual
-                Gaussian ids and tile-range positions are those of the chunk's sort, so rec / featp / grec / gfeat
-                are passed at the chunk's first view and only the per-view arrays are offset"""
+            def blend_bwd(k):
+                """backward blend of chunk k: one grid, blockIdx.z = view"""
                 b0, nb = chunks[k]
-                v0, nv = (b0, nb) if v0 is None else (v0, nv)
                 _lib.call("blend_backward", _blend_passes_bwd(cpad), L.msb_blend_packed_bwd_views, dev, ptr(rec[b0]),
-                          ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[v0 * T:]), bg, Pp, C, W, H, nv, ptr(final_T[v0]),
-                          ptr(ncontrib[v0]), ptr(g[v0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
+                          ptr(featp[b0]), ptr(ids_all[k]), ptr(tr[b0 * T:]), bg, Pp, C, W, H, nb, ptr(final_T[b0]),
+                          ptr(ncontrib[b0]), ptr(g[b0]), ptr(grec[b0]), ptr(gfeat[b0]), 1)
 
             def pre_bwd(v0, nv, lo, hi, accumulate, outs):
                 """fused preprocess backward of the views [v0, v0 + nv) for the Gaussians [lo, hi)"""
@@ -386,52 +380,40 @@ class _RenderSHViews(torch.autograd.Function):
                           ptr(dquat[lo:hi]), ptr(dop[lo:hi]), ptr(dshs[lo:hi]), ptr(dintr[v0]) if need_i else None,
                           ptr(dextr[v0]) if need_e else None)
 
-            def pieces(lo_v, hi_v):
-                """(chunk, first view, views) pieces covering the views [lo_v, hi_v)"""
-                out = []
-                for k, (b0, nb) in enumerate(chunks):
-                    a_, b_ = max(b0, lo_v), min(b0 + nb, hi_v)
-                    if a_ < b_:
-                        out.append((k, a_, b_ - a_))
-                return out
-
             dxyz = torch.empty((P, 3), dtype=f32, device=dev)
             dscale = torch.empty((P, 3), dtype=f32, device=dev)
             dquat = torch.empty((P, 4), dtype=f32, device=dev)
             dop = torch.empty((P,), dtype=f32, device=dev)
             dshs = torch.empty_like(sh)
             outs = (dxyz, dscale, dquat, dop, dshs)
-            # Schedule.  The views are split into a head and a tail (the last ~quarter).  The fused preprocess
-            # backward of the head (HBM-bound) runs on the side stream under the backward blend of the tail
-            # (issue-bound); the tail's own preprocess backward then adds into the same sums.  With grad_sync
-            # (view-batch data parallelism, SURVEY 8e) that last launch is cut into slabs of Gaussians and the sum
-            # all-reduce of a finished slab (NCCL, its own stream) runs under the kernels of the next slab.
-            ntail = max(1, B // 4) if (B >= 4 and ctx.overlap and BWD_SPLIT) else B
-            nhead = B - ntail
-            side = _side_stream(dev) if nhead > 0 else None
-            for k, v0, nv in pieces(0, nhead):
-                blend_bwd(k, v0, nv)
-            if side is not None:
-                side.wait_stream(main)  # the head's packed gradients; the outputs were allocated on `main`
-                with torch.cuda.stream(side):
-                    for j, (k, v0, nv) in enumerate(pieces(0, nhead)):
-                        pre_bwd(v0, nv, 0, P, j > 0, outs)
-            for k, v0, nv in pieces(nhead, B):
-                blend_bwd(k, v0, nv)
-            if side is not None:
-                main.wait_stream(side)
-            tail = pieces(nhead, B)
             if group is None:
-                for j, (k, v0, nv) in enumerate(tail):
-                    pre_bwd(v0, nv, 0, P, nhead > 0 or j > 0, outs)
+                # one chunk (the default): one backward blend grid, one fused preprocess backward launch.  Several
+                # chunks: the preprocess backward of chunk k (HBM-bound) on the side stream under the backward blend
+                # of chunk k + 1 (issue-bound)
+                side = _side_stream(dev) if (ctx.overlap and len(chunks) > 1) else None
+                if side is not None:
+                    side.wait_stream(main)  # the output tensors were allocated (and maybe recycled) on `main`
+                for k, (b0, nb) in enumerate(chunks):
+                    blend_bwd(k)
+                    with torch.cuda.stream(side if side is not None else main):
+                        if side is not None:
+                            side.wait_event(main.record_event())
+                        pre_bwd(b0, nb, 0, P, k > 0, outs)
+                if side is not None:
+                    main.wait_stream(side)
             else:
+                # view-batch data parallelism: all backward blends, then the preprocess backward slab by
+                # slab over the Gaussians; the sum all-reduce of a finished slab (its five tensors as ONE coalesced
+                # NCCL call, on NCCL's stream) runs under the kernels of the next slab
+                for k in range(len(chunks)):
+                    blend_bwd(k)
                 nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
                 step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
                 works = []
                 for lo in range(0, P, step):
                     hi = min(P, lo + step)
-                    for j, (k, v0, nv) in enumerate(tail):
-                        pre_bwd(v0, nv, lo, hi, nhead > 0 or j > 0, outs)
+                    for k, (b0, nb) in enumerate(chunks):
+                        pre_bwd(b0, nb, lo, hi, k > 0, outs)
                     works += _reduce_many(group, [t[lo:hi] for t in outs], dev)
                 for w in works:
                     if w is not None and hasattr(w, "wait"):

@@ -174,8 +174,7 @@ def test_render_sh_views_equals_single_views(ms):
 def test_render_sh_grad_sync_slabs(ms):
     """Data-parallel backward schedule: the reducer sees every gradient element exactly once, slab by slab (five
     tensors per slab), and what it does to a slab is what the caller gets back (here: x2, i.e. two identical
-    ranks).  Four views: the head/tail split of the backward (preprocess backward of the first views on the
-    side stream) is active."""
+    ranks)."""
     P, W, H, bg, deg, Cs, nv = 5003, 200, 136, 0.0, 3, 3, 4
     intr, extr = camera(W, H)
     extrs = torch.stack([extr.clone() for _ in range(nv)]).to(DEV)
