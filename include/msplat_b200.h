@@ -224,6 +224,16 @@ int msb_render_preprocess_bwd_views(const float* xyz, const float* scale, const 
                                     float* dL_dquat, float* dL_dopacity, float* dL_dshs, float* dL_dintr,
                                     float* dL_dextr, void* stream);
 
+/* ---- fused multi-tensor Adam --------------------------------------------------------------------
+ * replaces the per-tensor elementwise kernels of torch.optim.Adam in the reference's training loop
+ * (/root/reference/tutorials/gs_2d.py:32-36 optimizer over xyz/scale/rotate/opacity/rgb, :66-87 loop): ONE launch
+ * per 8 tensors.  torch.optim.Adam semantics (no weight decay, no amsgrad); params / grads / exp_avg /
+ * exp_avg_sq are HOST arrays of `ntensors` device pointers, numel a host array of element counts, `step` the
+ * 1-based step count of the bias corrections. */
+int msb_adam_step(int ntensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* numel, float lr, float beta1, float beta2, float eps,
+                  int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

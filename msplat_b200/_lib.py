@@ -61,6 +61,7 @@ def _declare(lib):
         "msb_compute_gaussian_key": (I, [P, P, P, P, I, LL, I, I, P, P, V]),
         "msb_compute_tile_gaussian_range": (I, [P, LL, I, I, P, V]),
         "msb_blend_pack": (I, [P, P, P, P, I, I, P, SZ, V]),
+        "msb_adam_step": (I, [I, P, P, P, P, P, F, F, F, F, I, V]),
         # view batches
         "msb_sort_num_passes_views": (I, [I, I, I]),
         "msb_sort_workspace_bytes_views": (SZ, [I, I, LL, I, I]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libmsplat_b200.so")
 
-SOURCES = ["capi.cu", "preprocess.cu", "sh.cu", "sort.cu", "blend.cu", "render.cu"]
+SOURCES = ["capi.cu", "preprocess.cu", "sh.cu", "sort.cu", "blend.cu", "render.cu", "adam.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,6 +18,9 @@ Fixtures written:
                            inputs / outputs / autograd gradients of the reference's torch
                            restatements (test/test_*.py) run on CPU (``.cuda()`` patched to a no-op)
                            at reduced N so the files stay small
+  gs2d_target.png          the 512x512 RGB target of the reference's 2-D fitting tutorial
+                           (tutorials/gs_2d.py:51 reads data/stanford-bunny.jpg), decoded once and stored
+                           losslessly so that the acceptance run (BASELINE config #2) fits the same pixels
 """
 import json
 import math
@@ -218,5 +221,15 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def gs2d_target():
+    from PIL import Image
+    im = Image.open(os.path.join(REF, "data", "stanford-bunny.jpg")).convert("RGB")
+    im.save(os.path.join(HERE, "gs2d_target.png"), optimize=True)
+    print("gs2d_target.png", im.size)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gs2d":
+        gs2d_target()
+        sys.exit(0)
     main()

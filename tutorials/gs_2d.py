@@ -5,10 +5,14 @@ Same experiment as the reference's tutorial (/root/reference/tutorials/gs_2d.py:
 activations, :48-64 seed / camera, :66-87 loop: Adam lr 0.01, SmoothL1 against the target, bg = 1),
 written against the drop-in API so that either library can run it:
 
-    python tutorials/gs_2d.py                       # msplat_b200, procedural 512x512 target
-    python tutorials/gs_2d.py --image bunny.jpg     # any RGB image (PIL)
-    python tutorials/gs_2d.py --library msplat      # the reference build, if importable
+    python tutorials/gs_2d.py                       # msplat_b200, the tutorial's 512x512 bunny target, fused Adam
+    python tutorials/gs_2d.py --image photo.jpg     # any RGB image (PIL)
+    python tutorials/gs_2d.py --library msplat      # the reference build, if importable (torch.optim.Adam)
+    python tutorials/gs_2d.py --optimizer torch     # torch.optim.Adam with msplat_b200
 
+The default target is the tutorial's own image (data/stanford-bunny.jpg of the reference, stored losslessly as
+tests/golden/gs2d_target.png); ``--image procedural`` selects a synthetic test card.  With msplat_b200 the
+optimizer step is ``msplat_b200.optim.FusedAdam`` (one launch over the five parameter tensors).
 No imageio / tqdm: progress goes to stdout, frames (optional) are written as PNGs with PIL.
 """
 from __future__ import annotations
@@ -39,9 +43,14 @@ def procedural_target(H: int, W: int) -> torch.Tensor:
     return img.clamp(0, 1)
 
 
+BUNNY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gs2d_target.png")
+
+
 def load_target(path: str | None, size: int) -> torch.Tensor:
-    if path is None:
+    if path == "procedural":
         return procedural_target(size, size)
+    if path is None:
+        path = BUNNY
     from PIL import Image
     import numpy as np
     im = np.asarray(Image.open(path).convert("RGB"), dtype="float32") / 255.0
@@ -71,23 +80,36 @@ def camera(W: int, H: int, device):
 
 
 def fit(api, target: torch.Tensor, points: int, iters: int, lr: float = 0.01, seed: int = 123, log_every: int = 100,
-        frames_dir: str | None = None, frame_every: int = 20, quiet: bool = False):
-    """Runs the optimisation; returns the list of losses (one float per iteration)."""
+        frames_dir: str | None = None, frame_every: int = 20, quiet: bool = False, optimizer: str = "torch",
+        timing: dict | None = None):
+    """Runs the optimisation; returns the list of losses (one float per iteration).  optimizer: "torch"
+    (torch.optim.Adam, gs_2d.py:32) or "fused" (msplat_b200.optim.FusedAdam: the same update in one launch)."""
     device = target.device
     _, H, W = target.shape
     g = torch.Generator().manual_seed(seed)
     params = make_parameters(points, device, g)
-    opt = torch.optim.Adam(list(params.values()), lr=lr)
+    if optimizer == "fused":
+        from msplat_b200.optim import FusedAdam
+        opt = FusedAdam(list(params.values()), lr=lr)
+    else:
+        opt = torch.optim.Adam(list(params.values()), lr=lr)
     intr, extr = camera(W, H, device)
     loss_fn = torch.nn.SmoothL1Loss()
     losses = []
     t0 = time.time()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timing is not None else None
+    loss_dev = []
     for it in range(iters):
+        if ev is not None and it == min(10, iters - 1):
+            ev[0].record()  # device time of the remaining iterations (the first ones warm the allocator up)
         image = api.rasterization(*activated(params), intr, extr, W, H, 1.0)
         loss = loss_fn(image, target)
         loss.backward()
         opt.step()
         opt.zero_grad()
+        if quiet and frames_dir is None:
+            loss_dev.append(loss.detach())  # no host sync per iteration
+            continue
         losses.append(float(loss.detach()))
         if frames_dir is not None and it % frame_every == 0:
             from PIL import Image
@@ -99,13 +121,20 @@ def fit(api, target: torch.Tensor, points: int, iters: int, lr: float = 0.01, se
             psnr = -10.0 * math.log10(max(mse, 1e-12))
             print(f"iter {it:5d}  loss {losses[-1]:.7f}  psnr {psnr:5.2f} dB  {(it + 1) / (time.time() - t0):7.1f} it/s",
                   flush=True)
+    if ev is not None:
+        ev[1].record()
+        torch.cuda.synchronize()
+        timing["ms_per_iteration"] = ev[0].elapsed_time(ev[1]) / max(iters - min(10, iters - 1), 1)
+    if loss_dev:
+        losses = [float(x) for x in torch.stack(loss_dev).cpu()]
     return losses
 
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--library", default="msplat_b200", help="module that provides rasterization()")
-    ap.add_argument("--image", default=None, help="RGB target image; default: a procedural test card")
+    ap.add_argument("--image", default=None, help="RGB target image; default: the tutorial's bunny; 'procedural': a test card")
+    ap.add_argument("--optimizer", default=None, choices=["torch", "fused"], help="default: fused with msplat_b200")
     ap.add_argument("--size", type=int, default=512, help="side of the procedural target")
     ap.add_argument("--points", type=int, default=10000)
     ap.add_argument("--iters", type=int, default=7000)
@@ -115,7 +144,8 @@ def main():
         raise SystemExit("gs_2d.py needs a CUDA device: the rasterizer has no CPU path")
     api = importlib.import_module(args.library)
     target = load_target(args.image, args.size).cuda()
-    losses = fit(api, target, args.points, args.iters, frames_dir=args.frames)
+    opt = args.optimizer or ("fused" if args.library == "msplat_b200" else "torch")
+    losses = fit(api, target, args.points, args.iters, frames_dir=args.frames, optimizer=opt)
     print(f"final loss {losses[-1]:.7f} (first {losses[0]:.7f})")
 
 
