@@ -112,20 +112,32 @@ def check(rc: int, what: str):
 TIMING = None
 
 
+def _invoke(what, fn, idx, args):
+    st = c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, st)
+        e1.record()
+        TIMING.append((what, e0, e1))
+        return rc
+    return fn(*args, st)
+
+
 def call(what: str, nlaunch: int, fn, device, *args):
-    """Invoke one C-ABI entry point on `device`'s current stream; raise on a non-zero status."""
+    """Invoke one C-ABI entry point on `device`'s current stream; raise on a non-zero status.  The kernels run
+    on the caller's current device: the device guard is only entered when `device` is not already current (the
+    guard and the Stream object are the bulk of the per-call host cost otherwise)."""
     global _launches
-    with torch.cuda.device(device):
-        st = stream_ptr(device)
-        if TIMING is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = fn(*args, st)
-            e1.record()
-            TIMING.append((what, e0, e1))
-        else:
-            rc = fn(*args, st)
-    check(rc, what)
+    idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+    cur = torch.cuda.current_device()
+    if idx is None or idx == cur:
+        rc = _invoke(what, fn, cur if idx is None else idx, args)
+    else:
+        with torch.cuda.device(idx):
+            rc = _invoke(what, fn, idx, args)
+    if rc != 0:
+        check(rc, what)
     with _count_lock:
         _launches += nlaunch
 
