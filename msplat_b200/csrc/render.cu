@@ -26,6 +26,8 @@
 // Algorithmic bytes per Gaussian at SH3 RGB+depth: forward 44 + 192*v in, 64 out;
 // backward 44 + 48 + 4 + 192*v in, 48 + 192 out (+ the same again when accumulating),
 // v = fraction of Gaussians that touch a tile.
+#include <stdlib.h>
+
 #include "blend_math.cuh"
 #include "geom.cuh"
 #include "sh_eval.cuh"
@@ -620,6 +622,410 @@ __global__ void __launch_bounds__(RP_NT, DEG <= 4 ? 4 : 2) render_pre_bwd_kernel
     if ((full && tid == 0) || filled) bulk_wait_read();  // shared memory stays valid until the copy engine has read it
 }
 
+// ------------------------------------------------------------------------------------------------
+// "PT" variants for short coefficient rows (degree 1 and 3, Cs * D <= 64 floats): the block's SH rows are
+// staged ONCE into shared memory (padded to an odd number of 16-byte units per row, so that 32 threads
+// reading their own rows with LDS.128 hit distinct banks) and reused by all views; the thread that owns a
+// Gaussian keeps the basis in registers and evaluates its colours itself.  Compared with the lane-group path
+// above this removes the per-view global row loads (the latency the block stalled on), the basis round trip
+// through shared memory, the survivor list and the shuffles: ~25 % fewer instructions per Gaussian and view, and
+// the rows come from HBM once per block instead of once per view.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int rp_pt_rs(int row_floats) { return ((row_floats / 4) | 1) * 4; }  // padded row stride
+constexpr int RP_PT_MAX_ROW = 64;  // floats per Gaussian (Cs * D) the PT kernels stage
+
+// stage `rows` coefficient rows of `rowf` floats (multiple of 4) into s_sh with row stride RS
+__device__ __forceinline__ void pt_stage_rows(float* __restrict__ s_sh, const float* __restrict__ shs, long long g0,
+                                              int rows, int rowf, int RS) {
+    const int units = rowf >> 2;
+    const float* src = shs + g0 * rowf;
+    for (int i = threadIdx.x; i < rows * units; i += RP_NT) {
+        const int r = i / units, u = i - r * units;
+        cp_async16(s_sh + r * RS + 4 * u, src + (long long)r * rowf + 4 * u);
+    }
+    cp_async_commit();
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(RP_NT, 2) render_pre_fwd_pt_kernel(
+    int P, int Cs, int Cpad, int with_depth, int views, long long vstride, const float* __restrict__ xyz,
+    const float* __restrict__ scale, const float* __restrict__ quat, const float* __restrict__ opacity,
+    const float* __restrict__ shs, const float* __restrict__ intr, const float* __restrict__ extr, int estride, int W,
+    int H, float nearest, float extent, float sh_bias, int clamp, float* __restrict__ rec, float* __restrict__ featp,
+    float* __restrict__ uv, float* __restrict__ depth, int* __restrict__ radius, int* __restrict__ tiles,
+    unsigned long long* __restrict__ total_tiles) {
+    constexpr int D = sh_dim(DEG);
+    constexpr int G = RP_NT;
+    static_assert(D % 4 == 0, "PT kernels need 16-byte coefficient units");
+    extern __shared__ __align__(16) float sm[];
+    float* s_xyz = sm;             // [G,3]   inputs: loaded once, read by every view
+    float* s_scale = sm + 3 * G;   // [G,3]
+    float* s_quat = sm + 6 * G;    // [G,4]
+    float* s_op = sm + 10 * G;     // [G]
+    float* s_rec = sm + 11 * G;    // [G,8]   outputs of the current view
+    float* s_uv = sm + 19 * G;     // [G,2]
+    float* s_feat = sm + 21 * G;   // [G,Cpad]
+    float* s_sh = s_feat + (size_t)Cpad * G;  // [G, RS] coefficient rows, staged once
+    __shared__ unsigned long long s_bar;
+    __shared__ unsigned int s_tsum;
+    const int rowf = Cs * D, RS = rp_pt_rs(rowf);
+
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * G;
+    const int rows = (int)min((long long)G, (long long)P - g0);
+    const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
+    const bool full = rows == G;
+    if (tid == 0 && full) mbar_init(&s_bar, 1);
+    __syncthreads();
+    pt_stage_rows(s_sh, shs, g0, rows, rowf, RS);
+    if (full) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)(11 * G * sizeof(float)));
+            bulk_g2s(s_xyz, xyz + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_scale, scale + g0 * 3, 3 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_quat, quat + g0 * 4, 4 * G * sizeof(float), &s_bar);
+            bulk_g2s(s_op, opacity + g0, G * sizeof(float), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+        slab_load<RP_NT>(s_op, opacity, g0, rows);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const int t = tid;
+    float px = 0.f, py = 0.f, pz = 0.f, op = 0.f;
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // cov3d does not depend on the camera: once per Gaussian
+    if (t < rows) {
+        px = s_xyz[3 * t];
+        py = s_xyz[3 * t + 1];
+        pz = s_xyz[3 * t + 2];
+        op = s_op[t];
+        const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
+        cov3d_fwd(s_scale[3 * t], s_scale[3 * t + 1], s_scale[3 * t + 2], q.x, q.y, q.z, q.w, cv);
+    }
+    const float4* my_sh = reinterpret_cast<const float4*>(s_sh + (size_t)t * RS);
+
+    for (int b = 0; b < views; ++b) {
+        const Cam c = load_cam(intr + 4 * b, extr + (size_t)estride * b);
+        const CamCenter cc = cam_center(c);
+        const long long v0 = (long long)b * vstride + g0;  // first output row of this block in view b
+        if (tid == 0) s_tsum = 0;
+        __syncthreads();  // also: the previous view's bulk stores have read the output slabs (thread 0 waited)
+
+        float u = 0.f, v = 0.f, d = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, hx = 0.f, hy = 0.f;
+        int rad = 0, til = 0;
+        if (t < rows) {
+            if (!project_fwd(c, px, py, pz, W, H, nearest, extent, u, v, d)) u = v = d = 0.f;
+            if (d != 0.f) {  // visible = depth != 0 (msplat/__init__.py:73)
+                if (!ewa_fwd(c, px, py, pz, cv, u, v, gx, gy, cx, cy, cz, rad, til)) {
+                    cx = cy = cz = 0.f;
+                    rad = til = 0;
+                }
+            }
+            float* f = s_feat + (size_t)t * Cpad;
+            for (int k = 0; k < Cpad; ++k) f[k] = 0.f;
+            if (with_depth) f[Cs] = d;
+            if (til > 0) {
+                float ex, ey, es, et;
+                cull_extent(cx, cy, cz, op, ex, ey, es, et);
+                cull_pack(ex, ey, es, et, hx, hy);  // hx, hy now hold the packed FP16 pairs of the blend record
+                const float rx = px - cc.x, ry = py - cc.y, rz = pz - cc.z;
+                const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+                float bs[D];
+                sh_basis<DEG>(rx * inv, ry * inv, rz * inv, bs, 1);
+                for (int ch = 0; ch < Cs; ++ch) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D / 4; ++k) {
+                        const float4 x = my_sh[ch * (D / 4) + k];
+                        acc = fmaf(x.x, bs[4 * k], acc);
+                        acc = fmaf(x.y, bs[4 * k + 1], acc);
+                        acc = fmaf(x.z, bs[4 * k + 2], acc);
+                        acc = fmaf(x.w, bs[4 * k + 3], acc);
+                    }
+                    float val = acc + sh_bias;
+                    if (clamp) val = fmaxf(val, 0.f);
+                    f[ch] = val;
+                }
+            }
+            float4* r = reinterpret_cast<float4*>(s_rec) + 2 * t;
+            r[0] = make_float4(u, v, cx, cy);
+            r[1] = make_float4(cz, op, hx, hy);
+            s_uv[2 * t] = u;
+            s_uv[2 * t + 1] = v;
+            depth[v0 + t] = d;
+            radius[v0 + t] = rad;
+            tiles[v0 + t] = til;
+        }
+        if (total_tiles != nullptr) {  // M = sum(tiles): sizes the sort output (replaces the separate count pass)
+            unsigned wsum = (unsigned)til;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            if ((tid & 31) == 0 && wsum) atomicAdd(&s_tsum, wsum);
+        }
+        if (full) {
+            fence_async_smem();  // this thread's slab writes -> visible to the bulk stores below
+            __syncthreads();
+            if (tid == 0) {
+                if (total_tiles != nullptr && s_tsum) atomicAdd(total_tiles + b, (unsigned long long)s_tsum);
+                bulk_s2g(rec + v0 * 8, s_rec, 8 * G * sizeof(float));
+                bulk_s2g(uv + v0 * 2, s_uv, 2 * G * sizeof(float));
+                bulk_s2g(featp + v0 * Cpad, s_feat, (unsigned)((size_t)Cpad * G * sizeof(float)));
+                bulk_commit();
+                bulk_wait_read();  // shared memory must stay valid until the copy engine has read it
+            }
+        } else {
+            __syncthreads();
+            if (tid == 0 && total_tiles != nullptr && s_tsum) atomicAdd(total_tiles + b, (unsigned long long)s_tsum);
+            slab_store<RP_NT>(rec, s_rec, v0 * 8, rows * 8);
+            slab_store<RP_NT>(uv, s_uv, v0 * 2, rows * 2);
+            slab_store<RP_NT>(featp, s_feat, v0 * Cpad, rows * Cpad);
+        }
+    }
+}
+
+template <int DEG, bool CAM>
+__global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
+    int P, int Cs, int Cpad, int with_depth, int accumulate, int views, long long vstride,
+    const float* __restrict__ xyz, const float* __restrict__ scale, const float* __restrict__ quat,
+    const float* __restrict__ shs, const float* __restrict__ intr, const float* __restrict__ extr, int estride,
+    float sh_bias, int clamp, const int* __restrict__ tiles, const float* __restrict__ grec,
+    const float* __restrict__ gfeat, float* __restrict__ dL_dxyz, float* __restrict__ dL_dscale,
+    float* __restrict__ dL_dquat, float* __restrict__ dL_dopacity, float* __restrict__ dL_dshs,
+    float* __restrict__ dL_dintr, float* __restrict__ dL_dextr) {
+    constexpr int D = sh_dim(DEG);
+    constexpr int G = RP_NT;
+    static_assert(D % 4 == 0, "PT kernels need 16-byte coefficient units");
+    extern __shared__ __align__(16) float sm[];
+    float* s_xyz = sm;             // [G,3]  -> dL_dxyz slab after the last view
+    float* s_scale = sm + 3 * G;   // [G,3]  -> dL_dscale slab
+    float* s_quat = sm + 6 * G;    // [G,4]  -> dL_dquat slab
+    float* s_gin = sm + 10 * G;    // [2][G, 8 + Cpad]  packed gradients of the current / next view
+    const int gin_stride = (8 + Cpad) * G;
+    float* s_sh = s_gin + 2 * gin_stride;  // [G, RS] coefficient rows, staged once
+    __shared__ float s_red[8 * 16];
+    __shared__ unsigned long long s_bar[3];  // inputs | gradient buffer 0 | gradient buffer 1
+    const int rowf = Cs * D, RS = rp_pt_rs(rowf);
+
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * G;
+    const int rows = (int)min((long long)G, (long long)P - g0);
+    const bool full = rows == G;
+    if (tid == 0 && full) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+    }
+    __syncthreads();
+    pt_stage_rows(s_sh, shs, g0, rows, rowf, RS);
+    const unsigned gin_bytes = (unsigned)((size_t)(8 + Cpad) * G * sizeof(float));
+    auto prefetch = [&](int b) {  // thread 0 of a full block: packed gradients of view b -> buffer b & 1
+        float* dst = s_gin + (b & 1) * gin_stride;
+        const long long v0 = (long long)b * vstride + g0;
+        mbar_expect_tx(&s_bar[1 + (b & 1)], gin_bytes);
+        bulk_g2s(dst, grec + v0 * 8, 8 * G * sizeof(float), &s_bar[1 + (b & 1)]);
+        bulk_g2s(dst + 8 * G, gfeat + v0 * Cpad, (unsigned)((size_t)Cpad * G * sizeof(float)), &s_bar[1 + (b & 1)]);
+    };
+    if (full) {
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar[0], (unsigned)(10 * G * sizeof(float)));
+            bulk_g2s(s_xyz, xyz + g0 * 3, 3 * G * sizeof(float), &s_bar[0]);
+            bulk_g2s(s_scale, scale + g0 * 3, 3 * G * sizeof(float), &s_bar[0]);
+            bulk_g2s(s_quat, quat + g0 * 4, 4 * G * sizeof(float), &s_bar[0]);
+            prefetch(0);
+        }
+        mbar_wait(&s_bar[0], 0);
+    } else {
+        slab_load<RP_NT>(s_xyz, xyz, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_scale, scale, g0 * 3, rows * 3);
+        slab_load<RP_NT>(s_quat, quat, g0 * 4, rows * 4);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int t = tid;
+    const float4* my_sh = reinterpret_cast<const float4*>(s_sh + (size_t)t * RS);
+    float* my_out = dL_dshs + (g0 + t) * (long long)rowf;  // this Gaussian's dL_dshs row
+    // geometry gradients, summed over the views in registers
+    float dx = 0.f, dy = 0.f, dz = 0.f, dop = 0.f;
+    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int b = 0; b < views; ++b) {
+        const Cam c = load_cam(intr + 4 * b, extr + (size_t)estride * b);
+        const CamCenter cc = cam_center(c);
+        const long long v0 = (long long)b * vstride + g0;
+        float* s_grec = s_gin + (b & 1) * gin_stride;   // [G,8]
+        float* s_gfeat = s_grec + 8 * G;                // [G,Cpad]
+        const bool acc_b = accumulate || b > 0;
+        if (full) {
+            // every thread is past its reads of the other buffer (barrier at the end of the previous view)
+            if (tid == 0 && b + 1 < views) prefetch(b + 1);
+            mbar_wait(&s_bar[1 + (b & 1)], (unsigned)((b >> 1) & 1));
+        } else {
+            slab_load<RP_NT>(s_grec, grec, v0 * 8, rows * 8);
+            slab_load<RP_NT>(s_gfeat, gfeat, v0 * Cpad, rows * Cpad);
+            __syncthreads();
+        }
+        float cam[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cam[i] = 0.f;
+        if (t < rows) {
+            const bool vis = tiles[v0 + t] > 0;
+            const float px = s_xyz[3 * t], py = s_xyz[3 * t + 1], pz = s_xyz[3 * t + 2];
+            const float* gf = s_gfeat + (size_t)t * Cpad;
+            bool live = false;
+            if (vis)
+                for (int k = 0; k < Cs; ++k) live = live || (gf[k] != 0.f);
+            float ax = 0.f, ay = 0.f, az = 0.f;
+            if (live) {
+                const float rx = px - cc.x, ry = py - cc.y, rz = pz - cc.z;
+                const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+                const float dirx = rx * inv, diry = ry * inv, dirz = rz * inv;
+                float bs[D], w[D];
+                sh_basis<DEG>(dirx, diry, dirz, bs, 1);
+#pragma unroll
+                for (int i = 0; i < D; ++i) w[i] = 0.f;
+                for (int ch = 0; ch < Cs; ++ch) {
+                    float sv[D];
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D / 4; ++k) {
+                        const float4 x = my_sh[ch * (D / 4) + k];
+                        sv[4 * k] = x.x; sv[4 * k + 1] = x.y; sv[4 * k + 2] = x.z; sv[4 * k + 3] = x.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) acc = fmaf(sv[i], bs[i], acc);
+                    // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
+                    const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gf[ch];
+                    float* op = my_out + ch * D;
+#pragma unroll
+                    for (int k = 0; k < D / 4; ++k) {
+                        const float o0 = bs[4 * k] * dv, o1 = bs[4 * k + 1] * dv, o2 = bs[4 * k + 2] * dv, o3 = bs[4 * k + 3] * dv;
+                        if (acc_b) {
+                            if (dv != 0.f) red_add_v4(op + 4 * k, o0, o1, o2, o3);  // no read of the old row
+                        } else {
+                            *reinterpret_cast<float4*>(op + 4 * k) = make_float4(o0, o1, o2, o3);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) w[i] = fmaf(sv[i], dv, w[i]);
+                }
+                float hx, hy, hz;  // dL_ddir
+                sh_basis_grad<DEG>(dirx, diry, dirz, w, 1, hx, hy, hz);
+                // dir = r / |r|  =>  dL_dr = (g - dir (dir . g)) / |r|
+                const float dt = dirx * hx + diry * hy + dirz * hz;
+                ax = (hx - dirx * dt) * inv;
+                ay = (hy - diry * dt) * inv;
+                az = (hz - dirz * dt) * inv;
+                if (CAM) {
+                    // r = p - centre, centre = -R^T t  =>  dL_dR[i][j] += dL_dr[j] t[i], dL_dt[i] += R[i][:] . dL_dr
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float ti = c.e[4 * i + 3];
+                        cam[4 + 4 * i + 0] += ax * ti;
+                        cam[4 + 4 * i + 1] += ay * ti;
+                        cam[4 + 4 * i + 2] += az * ti;
+                        cam[4 + 4 * i + 3] += c.e[4 * i] * ax + c.e[4 * i + 1] * ay + c.e[4 * i + 2] * az;
+                    }
+                }
+            } else if (!acc_b) {
+                // write mode: every row of dL_dshs must be produced (zeros for untouched Gaussians)
+                for (int k = 0; k < rowf / 4; ++k) reinterpret_cast<float4*>(my_out)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (vis) {
+                const float4 ga = reinterpret_cast<const float4*>(s_grec)[2 * t];      // dL_duv, dL_dconic.xy
+                const float4 gb = reinterpret_cast<const float4*>(s_grec)[2 * t + 1];  // dL_dconic.z, dL_dopacity
+                dop += gb.y;
+                const float gd = with_depth ? gf[Cs] : 0.f;
+                float bx, by, bz;
+                project_bwd<CAM>(c, px, py, pz, ga.x, ga.y, gd, bx, by, bz, cam);
+                ax += bx;
+                ay += by;
+                az += bz;
+                const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
+                const float sx = s_scale[3 * t], sy = s_scale[3 * t + 1], sz = s_scale[3 * t + 2];
+                float cv[6], dcv[6], ex, ey, ez;
+                cov3d_fwd(sx, sy, sz, q.x, q.y, q.z, q.w, cv);
+                if (ewa_bwd<CAM>(c, px, py, pz, cv, ga.z, ga.w, gb.x, ex, ey, ez, dcv, cam)) {
+                    ax += ex;
+                    ay += ey;
+                    az += ez;
+                    float vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f};
+                    cov3d_bwd(sx, sy, sz, q.x, q.y, q.z, q.w, dcv, vs, vq);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) ds[i] += vs[i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dq[i] += vq[i];
+                }
+                dx += ax;
+                dy += ay;
+                dz += az;
+            }
+        }
+        if (CAM) cam_reduce_atomic<RP_NT>(cam, dL_dintr ? dL_dintr + 4 * b : nullptr,
+                                          dL_dextr ? dL_dextr + (size_t)estride * b : nullptr, s_red);
+        __syncthreads();  // this view's gradient buffer may now be overwritten
+    }
+
+    if (t < rows) {
+        s_xyz[3 * t] = dx;
+        s_xyz[3 * t + 1] = dy;
+        s_xyz[3 * t + 2] = dz;
+        s_scale[3 * t] = ds[0];
+        s_scale[3 * t + 1] = ds[1];
+        s_scale[3 * t + 2] = ds[2];
+        reinterpret_cast<float4*>(s_quat)[t] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        if (accumulate) {
+            if (dop != 0.f) atomicAdd(dL_dopacity + g0 + t, dop);  // result unused -> RED
+        } else {
+            dL_dopacity[g0 + t] = dop;
+        }
+    }
+    if (full) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (accumulate) {
+                bulk_s2g_add_f32(dL_dxyz + g0 * 3, s_xyz, 3 * G * sizeof(float));
+                bulk_s2g_add_f32(dL_dscale + g0 * 3, s_scale, 3 * G * sizeof(float));
+                bulk_s2g_add_f32(dL_dquat + g0 * 4, s_quat, 4 * G * sizeof(float));
+            } else {
+                bulk_s2g(dL_dxyz + g0 * 3, s_xyz, 3 * G * sizeof(float));
+                bulk_s2g(dL_dscale + g0 * 3, s_scale, 3 * G * sizeof(float));
+                bulk_s2g(dL_dquat + g0 * 4, s_quat, 4 * G * sizeof(float));
+            }
+            bulk_commit();
+            bulk_wait_read();
+        }
+    } else {
+        __syncthreads();
+        if (accumulate) {
+            slab_store_acc<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+            slab_store_acc<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+            slab_store_acc<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+        } else {
+            slab_store<RP_NT>(dL_dxyz, s_xyz, g0 * 3, rows * 3);
+            slab_store<RP_NT>(dL_dscale, s_scale, g0 * 3, rows * 3);
+            slab_store<RP_NT>(dL_dquat, s_quat, g0 * 4, rows * 4);
+        }
+    }
+}
+
+static size_t rp_pt_smem_fwd(int Cs, int D, int Cpad) {
+    return ((size_t)21 * RP_NT + (size_t)Cpad * RP_NT + (size_t)rp_pt_rs(Cs * D) * RP_NT) * sizeof(float);
+}
+static size_t rp_pt_smem_bwd(int Cs, int D, int Cpad) {
+    return ((size_t)10 * RP_NT + 2 * (size_t)(8 + Cpad) * RP_NT + (size_t)rp_pt_rs(Cs * D) * RP_NT) * sizeof(float);
+}
+// PT path: degree 1 or 3, rows of at most RP_PT_MAX_ROW floats, 16-byte aligned rows; MSB_RP_PT=0 disables (A/B)
+static bool rp_use_pt(int deg, int Cs) {
+    static const int on = [] { const char* e = getenv("MSB_RP_PT"); return e ? atoi(e) : 1; }();
+    return on && (deg == 1 || deg == 3) && Cs > 0 && Cs * sh_dim(deg) <= RP_PT_MAX_ROW;
+}
+
 static size_t rp_smem_fwd(int deg, int Cpad) {
     const int G = rp_gpb(deg);
     return ((size_t)21 * G + rp_bs(deg) + (size_t)Cpad * G + G) * sizeof(float);
@@ -642,7 +1048,25 @@ struct RpFwdArgs {
 };
 
 template <int DEG>
+static int rp_launch_fwd_pt(const RpFwdArgs& a, cudaStream_t st) {
+    const size_t smem = rp_pt_smem_fwd(a.Cs, sh_dim(DEG), a.Cpad);
+    cudaError_t e = cudaFuncSetAttribute(render_pre_fwd_pt_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return set_error((int)e, "render_preprocess_fwd: cudaFuncSetAttribute failed");
+    const unsigned grid = (unsigned)(((long long)a.P + RP_NT - 1) / RP_NT);
+    render_pre_fwd_pt_kernel<DEG><<<grid, RP_NT, smem, st>>>(a.P, a.Cs, a.Cpad, a.with_depth, a.views, a.vstride, a.xyz,
+                                                             a.scale, a.quat, a.opacity, a.shs, a.intr, a.extr,
+                                                             a.estride, a.W, a.H, a.nearest, a.extent, a.sh_bias, a.clamp,
+                                                             a.rec, a.featp, a.uv, a.depth, a.radius, a.tiles,
+                                                             a.total_tiles);
+    return check_launch("render_preprocess_fwd");
+}
+
+template <int DEG>
 static int rp_launch_fwd(const RpFwdArgs& a, cudaStream_t st) {
+    if constexpr (DEG == 1 || DEG == 3) {
+        if (rp_use_pt(DEG, a.Cs) && rp_pt_smem_fwd(a.Cs, sh_dim(DEG), a.Cpad) <= 100 * 1024) return rp_launch_fwd_pt<DEG>(a, st);
+    }
     const size_t smem = rp_smem_fwd(DEG, a.Cpad);
     if (smem > 200 * 1024) return set_error(MSB_ERR_RANGE, "render_preprocess_fwd: too many channels for shared memory");
     if (smem > 48 * 1024) {
@@ -672,7 +1096,24 @@ struct RpBwdArgs {
 };
 
 template <int DEG, bool CAM>
+static int rp_launch_bwd_pt(const RpBwdArgs& a, cudaStream_t st) {
+    const size_t smem = rp_pt_smem_bwd(a.Cs, sh_dim(DEG), a.Cpad);
+    cudaError_t e = cudaFuncSetAttribute(render_pre_bwd_pt_kernel<DEG, CAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return set_error((int)e, "render_preprocess_bwd: cudaFuncSetAttribute failed");
+    const unsigned grid = (unsigned)(((long long)a.P + RP_NT - 1) / RP_NT);
+    render_pre_bwd_pt_kernel<DEG, CAM><<<grid, RP_NT, smem, st>>>(
+        a.P, a.Cs, a.Cpad, a.with_depth, a.accumulate, a.views, a.vstride, a.xyz, a.scale, a.quat, a.shs, a.intr,
+        a.extr, a.estride, a.sh_bias, a.clamp, a.tiles, a.grec, a.gfeat, a.dxyz, a.dscale, a.dquat, a.dopacity, a.dshs,
+        a.dintr, a.dextr);
+    return check_launch("render_preprocess_bwd");
+}
+
+template <int DEG, bool CAM>
 static int rp_launch_bwd(const RpBwdArgs& a, cudaStream_t st) {
+    if constexpr (DEG == 1 || DEG == 3) {
+        if (rp_use_pt(DEG, a.Cs) && rp_pt_smem_bwd(a.Cs, sh_dim(DEG), a.Cpad) <= 110 * 1024) return rp_launch_bwd_pt<DEG, CAM>(a, st);
+    }
     const size_t smem = rp_smem_bwd(DEG, a.Cpad);
     if (smem > 200 * 1024) return set_error(MSB_ERR_RANGE, "render_preprocess_bwd: too many channels for shared memory");
     if (smem > 48 * 1024) {

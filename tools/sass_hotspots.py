@@ -37,7 +37,8 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "msplat_b200", "libmsplat_b200.so")], cwd=tmp,
                    capture_output=True)
-    short = re.sub(r"\(.*", "", name).replace("void ", "")
+    norm = lambda n: re.sub(r"\(.*", "", n.replace("(int)", "").replace("(bool)", "")).replace("void ", "").replace(" ", "")
+    short = norm(name)
     best = None
     for f in os.listdir(tmp):
         txt = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, f)], capture_output=True, text=True).stdout
@@ -49,7 +50,7 @@ def main():
             if not m:
                 continue
             dem = subprocess.run(["cu++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            if re.sub(r"\(.*", "", dem).replace("void ", "") == short:
+            if norm(dem) == short:
                 ins, cur = [], ("?", 0)
                 for l2 in lines[i + 1:]:
                     if l2.startswith(".text.") and "L_x" not in l2 and ins:
