@@ -23,7 +23,11 @@ def shard_views(n_views: int, rank: int, world: int) -> range:
 
 class FlatGrads:
     """One contiguous gradient buffer whose slices are the ``.grad`` of the given leaf tensors, so
-    that local accumulation over views happens in place and the step needs ONE all-reduce."""
+    that local accumulation over views happens in place and the step needs ONE all-reduce.
+
+    The ``.grad`` views must stay attached: clear gradients with :meth:`zero_` (or
+    ``optimizer.zero_grad(set_to_none=False)``), not with ``zero_grad()``'s default ``set_to_none=True``, which
+    would detach them -- :meth:`all_reduce` checks this and raises instead of silently reducing stale zeros."""
 
     def __init__(self, params: Sequence[torch.Tensor]):
         self.params = list(params)
@@ -50,7 +54,15 @@ class FlatGrads:
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
 
+    def attached(self) -> bool:
+        """every parameter's .grad is still its slice of the flat buffer"""
+        base, esz = self.flat.data_ptr(), self.flat.element_size()
+        return all(p.grad is not None and p.grad.data_ptr() == base + o * esz for p, (o, n) in zip(self.params, self.offsets))
+
     def all_reduce(self, async_op: bool = False):
+        if not self.attached():
+            raise RuntimeError("FlatGrads: a parameter's .grad no longer points into the flat buffer (zero_grad("
+                               "set_to_none=True)?): call attach() before the backward passes, clear with zero_()")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return None

@@ -70,3 +70,24 @@ def test_two_rank_allreduce_matches_single_process():
     for rank, flat, _ in out:
         torch.testing.assert_close(flat, grads.flat, rtol=1e-5, atol=1e-6)
     assert abs(out[0][2] + out[1][2] - float(total)) < 1e-3 * abs(float(total))
+
+
+def test_flat_grads_detached_views_are_caught():
+    """zero_grad(set_to_none=True) detaches the .grad views from the flat buffer: all_reduce must not silently
+    reduce stale zeros."""
+    import pytest
+    xyz, w = _make_params()
+    grads = FlatGrads([xyz, w])
+    (xyz.sum() + w.sum()).backward()
+    assert grads.attached() and float(grads.flat.sum()) == xyz.numel() + w.numel()
+    grads.all_reduce()  # world size 1: no collective, but the check runs
+    xyz.grad = None     # what optimizer.zero_grad() does by default
+    (xyz.sum() + w.sum()).backward()
+    assert not grads.attached()
+    with pytest.raises(RuntimeError, match="flat buffer"):
+        grads.all_reduce()
+    grads.attach()
+    grads.zero_()
+    (xyz.sum() + w.sum()).backward()
+    grads.all_reduce()
+    assert float(grads.flat.sum()) == xyz.numel() + w.numel()
