@@ -348,13 +348,12 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int Pv /*Gaussians
 // ------------------------------------------------------------------------------------------------
 // phase 2c: start offsets in depth order -- single-pass chained scan of n[order[i]] (+ Z)
 // ------------------------------------------------------------------------------------------------
-// One kernel instead of block sums + spine + apply: the 4-byte gathers rect[order[i]].n (one 32-byte
-// sector each) are done once.  Tiles of 2048 are taken by ticket; warp 0 resolves the tile's
+// One kernel instead of block sums + spine + apply.  The emitted counts come from the depth-ordered records the
+// last depth pass wrote (no gather here).  Tiles of 2048 are taken by ticket; warp 0 resolves the tile's
 // exclusive prefix by decoupled look-back over one (flag | inclusive prefix) word per tile, 32
 // predecessors per round trip.
 __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int* __restrict__ n_dev,
-                                                             const int4* __restrict__ rect,
-                                                             const int* __restrict__ order,
+                                                             const int4* __restrict__ rsorted /*depth order {x0|w<<16, y0, n, id}*/,
                                                              const unsigned int* __restrict__ zcount,
                                                              int* __restrict__ start,
                                                              unsigned int* __restrict__ status,
@@ -369,13 +368,11 @@ __global__ void __launch_bounds__(SC_NT) scan_offsets_kernel(const unsigned int*
     const long long base = (long long)tile * SC_TILE + (long long)threadIdx.x * SC_IPT;
     if ((long long)tile * SC_TILE >= N) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int id[SC_IPT], v[SC_IPT];
-#pragma unroll
-    for (int k = 0; k < SC_IPT; ++k) id[k] = base + k < N ? order[base + k] : -1;
+    int v[SC_IPT];
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < SC_IPT; ++k) {
-        v[k] = id[k] >= 0 ? rect[id[k]].w : 0;
+        v[k] = base + k < N ? rsorted[base + k].z : 0;
         sum += v[k];
     }
     int total;
@@ -457,8 +454,7 @@ __device__ __forceinline__ void dup_hist(unsigned int* s_hist, unsigned int tile
 }
 
 __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* __restrict__ pcount,
-                                                           const int* __restrict__ order /*[Pc] depth order*/,
-                                                           const int4* __restrict__ rect /*[P] {x0, y0, w, n}*/,
+                                                           const int4* __restrict__ rsorted /*[Pc] depth order {x0|w<<16, y0, n, id}*/,
                                                            const int* __restrict__ start_sorted, int gx, int npass,
                                                            const unsigned int* __restrict__ zcount,
                                                            unsigned int* __restrict__ keys, int* __restrict__ vals,
@@ -482,13 +478,13 @@ __global__ void __launch_bounds__(DUP_NT) duplicate_kernel(const unsigned int* _
         const long long i = chunk * DUP_NT + threadIdx.x;
         int n = 0, start = 0, x0 = 0, y0 = 0, w = 1, id = 0;
         if (i < P) {
-            id = order[i];
             start = start_sorted[i];
-            const int4 r = rect[id];  // one 16-byte gather per Gaussian
-            x0 = r.x;
+            const int4 r = rsorted[i];  // sequential: the last depth pass gathered the record
+            x0 = r.x & 0xffff;
+            w = (int)((unsigned)r.x >> 16);
             y0 = r.y;
-            w = r.z;
-            n = r.w;
+            n = r.z;
+            id = r.w;
         }
         // ---- footprints of up to DUP_COOP tiles: load-balanced expansion ----------------------------------
         // The warp's Gaussians own consecutive output runs; lane L emits entry e = base + L of the
@@ -605,13 +601,18 @@ __device__ __forceinline__ void peer_bit(unsigned d, unsigned& m) {
 // IPT: keys per thread (16).  A/B on BASELINE config #3 (profiles/r1_ab_experiments.md): 8 keys per thread
 // at 6 CTAs/SM and look-back windows of 16 / 32 were not faster for the L2-resident depth passes;
 // what helped them was the single-lane wait below (gate_ns).
-template <bool DEVN, int LB, int NB, int IPT>
+// GATHER (last depth pass): while scattering, the kernel also fetches the tile rectangle of every Gaussian
+// (rect[id], the pipeline's one random gather) and writes it, with the id, at the Gaussian's depth-order position:
+// rsorted[pos] = {x0 | w << 16, y0, n, id} -- the offset scan and the duplication then stream sequentially.
+template <bool DEVN, int LB, int NB, int IPT, bool GATHER = false>
 __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int N, const unsigned int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ kin,
                                                             const int* __restrict__ vin,
                                                             unsigned int* __restrict__ kout, int* __restrict__ vout,
                                                             const unsigned int* __restrict__ hist /*[256] this pass*/,
                                                             unsigned int* __restrict__ status /*[ntiles][256]*/,
-                                                            unsigned int* __restrict__ ticket, int gate_ns) {
+                                                            unsigned int* __restrict__ ticket, int gate_ns,
+                                                            const int4* __restrict__ rect = nullptr,
+                                                            int4* __restrict__ rsorted = nullptr) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
     RsSmem<IPT>& sm = *reinterpret_cast<RsSmem<IPT>*>(rs_raw);
     constexpr int TILE = RS_NT * IPT;
@@ -761,8 +762,14 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
         const unsigned int k = sm.keys[j];  // rotated key
         const unsigned d = k & 255u;
         const long long g = (long long)sm.gadj[d] + j;
-        kout[g] = __funnelshift_l(k, k, shift);
-        vout[g] = sm.vals[j];
+        if (GATHER) {
+            const int id = sm.vals[j];
+            const int4 r = rect[id];
+            rsorted[g] = make_int4(r.x | (r.z << 16), r.y, r.w, id);
+        } else {
+            kout[g] = __funnelshift_l(k, k, shift);
+            vout[g] = sm.vals[j];
+        }
     }
 }
 
@@ -811,7 +818,7 @@ static int tile_bits(int T) {
 static int tile_passes(int T) { return (tile_bits(T) + 7) / 8; }
 
 struct SortLayout {
-    size_t dkeys[2], dvals[2], rect, start, tkeys[2], tvals, zero0, hist, ticket, zcount, pcount, status_k, status_s, status_d, status_t,
+    size_t dkeys[2], dvals[2], rect, rsorted, start, tkeys[2], tvals, zero0, hist, ticket, zcount, pcount, status_k, status_s, status_d, status_t,
         total;
     int tpass, ntiles_d, ntiles_t, nb_scan, nchunks_k;
 };
@@ -832,6 +839,7 @@ static SortLayout sort_layout(int P, long long M, int T) {
     for (int k = 0; k < 2; ++k) L.dkeys[k] = take((size_t)P * 4);
     for (int k = 0; k < 2; ++k) L.dvals[k] = take((size_t)P * 4);
     L.rect = take((size_t)P * 16);
+    L.rsorted = take((size_t)P * 16);
     L.start = take((size_t)P * 4);
     for (int k = 0; k < 2; ++k) L.tkeys[k] = take((size_t)M * 4);
     L.tvals = take((size_t)M * 4);
@@ -975,6 +983,7 @@ int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* 
         return set_error(MSB_ERR_ARG, "sort_gaussian: bad argument");
     if ((long long)Pv * views > INT32_MAX || (long long)gx * gy * views > INT32_MAX)
         return set_error(MSB_ERR_RANGE, "sort_gaussian: views * P and views * tiles must stay below 2^31");
+    if (gx >= 65536) return set_error(MSB_ERR_RANGE, "sort_gaussian: more than 65535 tile columns (W >= 2^20 pixels)");
     // int32 positions, like the reference's int32 cumsum (msplat/sort_gaussian.py:42)
     if (M > (long long)INT32_MAX) return set_error(MSB_ERR_RANGE, "sort_gaussian: more than 2^31 - 1 tile intersections");
     const int P = Pv * views;
@@ -1024,16 +1033,21 @@ int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* 
         unsigned int* kout = U32(L.dkeys[(p + 1) % 2]);
         int* vout = I32(L.dvals[(p + 1) % 2]);
         unsigned int* stat = U32(L.status_d) + (size_t)p * L.ntiles_d * 256;
-        onesweep_kernel<true, 8, 8, RS_IPT><<<ntiles_d, RS_NT, sizeof(RsSmem<RS_IPT>), st>>>(
-            P, pcount, 8 * p, kin, vin, kout, vout, hist + p * 256, stat, ticket + p, gate_ns);
+        if (p < 3)
+            onesweep_kernel<true, 8, 8, RS_IPT><<<ntiles_d, RS_NT, sizeof(RsSmem<RS_IPT>), st>>>(
+                P, pcount, 8 * p, kin, vin, kout, vout, hist + p * 256, stat, ticket + p, gate_ns);
+        else  // the last depth pass writes the depth-ordered {rectangle, id} records instead of (key, id)
+            onesweep_kernel<true, 8, 8, RS_IPT, true><<<ntiles_d, RS_NT, sizeof(RsSmem<RS_IPT>), st>>>(
+                P, pcount, 8 * p, kin, vin, kout, vout, hist + p * 256, stat, ticket + p, gate_ns,
+                reinterpret_cast<const int4*>(base + L.rect), reinterpret_cast<int4*>(base + L.rsorted));
         rc = check_launch("sort_gaussian/onesweep(depth)");
         if (rc) return rc;
     }
-    const int* order = I32(L.dvals[0]);
+    const int4* rsorted = reinterpret_cast<const int4*>(base + L.rsorted);
 
     // 2c: start offsets in depth order (exclusive scan of the emitted counts, + Z)
-    scan_offsets_kernel<<<nb_scan, SC_NT, 0, st>>>(pcount, reinterpret_cast<const int4*>(base + L.rect), order, zcount,
-                                                   I32(L.start), U32(L.status_s), ticket + 4 + MAX_TPASS + 1);
+    scan_offsets_kernel<<<nb_scan, SC_NT, 0, st>>>(pcount, rsorted, zcount, I32(L.start), U32(L.status_s),
+                                                   ticket + 4 + MAX_TPASS + 1);
     rc = check_launch("sort_gaussian/offsets");
     if (rc) return rc;
 
@@ -1044,8 +1058,7 @@ int msb_sort_gaussian_views(const float* uv, const float* depth, const int32_t* 
     tv[(L.tpass + 1) % 2] = I32(L.tvals);
     unsigned int* thist = hist + 4 * 256;
     const unsigned dgrid = (unsigned)max(1ll, min((pc_max + DUP_NT - 1) / DUP_NT, (long long)sms * 8));
-    duplicate_kernel<<<dgrid, DUP_NT, 0, st>>>(pcount, order, reinterpret_cast<const int4*>(base + L.rect), I32(L.start),
-                                               gx, L.tpass, zcount, tk[0], tv[0], thist);
+    duplicate_kernel<<<dgrid, DUP_NT, 0, st>>>(pcount, rsorted, I32(L.start), gx, L.tpass, zcount, tk[0], tv[0], thist);
     rc = check_launch("sort_gaussian/duplicate");
     if (rc) return rc;
 
