@@ -26,19 +26,23 @@
 //                        kept, no chained scan) into (depth key, id) pairs; per Gaussian a 16-byte
 //                        record {x0, y0, w, n} of its tile rectangle; digit histograms of the 4 depth
 //                        passes; phantom-slot count Z.  Pc stays on the device.
-//   phase 2b onesweep  : 4 passes of 8 bits over (depth key, Gaussian id), Pc elements, L2-resident;
+//   phase 2b onesweep  : 4 passes of 8 bits over (depth key, Gaussian id), Pc elements;
 //                        each pass is ONE kernel: ballot-built peer masks -> ranks in shared-memory
 //                        histograms, chained scan with decoupled look-back on a (value|flag) word per
-//                        digit, keys exchanged through shared memory so global writes are coalesced
-//   phase 2c offsets   : single-pass chained exclusive scan of n in depth order (+Z)
-//   phase 2d duplicate : warp-cooperative emission of (tile id, Gaussian id) in depth order; the
-//                        histograms of the tile passes are accumulated on the fly
+//                        digit, keys exchanged through shared memory so global writes are coalesced;
+//                        the LAST pass writes, instead of (key, id), the depth-ordered records
+//                        {x0 | w << 16, y0, n, id}: the pipeline's one random gather (rect[id])
+//   phase 2c offsets   : single-pass chained exclusive scan of n in depth order (+Z), sequential reads
+//   phase 2d duplicate : warp-cooperative emission of (tile id, Gaussian id) in depth order from the
+//                        records (sequential reads); the histograms of the tile passes are accumulated on the fly
 //   phase 2e onesweep  : ceil(bits(T-1)/8) passes over (tile id, Gaussian id), M elements; the top
 //                        digit compares only the bits the tile ids use
 //   phase 2f ranges    : boundary detection on the sorted tile ids
 // Algorithmic bytes: 20 B/Gaussian keygen reads (+20 again from L2) + per emitter 8 B pair + 16 B
-//                    record, 4 * 16 B/emitter depth passes, 28 B/emitter offsets + duplicate reads,
+//                    record, 4 * 16 B/emitter depth passes (the last: + 16 B gather, 16 B record instead of
+//                    the 8 B pair), 16 + 4 B/emitter offsets, 20 B/emitter duplicate reads,
 //                    8 B/key duplicate write + pt * 16 B/key + 4 B/key ranges.
+// View batches: the arrays hold views * P entries; see keygen_kernel.
 #include <stdlib.h>
 
 #include "geom.cuh"
