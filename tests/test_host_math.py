@@ -198,3 +198,19 @@ def test_cull_extent_fp16_packing_rounds_up(host_check):
     fin = np.isfinite(vals) & (vals > 1e-3) & (vals < 6e4)
     assert (out[fin] <= vals[fin] * (1 + 2.0 ** -10)).all()  # at most one FP16 ulp of slack
     assert np.isposinf(out[vals > 65504.0]).all() and np.isneginf(out[np.isneginf(vals)]).all()
+
+
+def test_view_batch_chunking_host_logic():
+    """msplat_b200/render.py: how a view batch is cut into chunks, and how chunks whose views hold more than
+    2^31 - 1 tile intersections together are split again before anything is queued."""
+    from msplat_b200.render import M_MAX, _chunks, _split_for_sort
+    assert _chunks(8, 0) == [(0, 8)] and _chunks(8, 3) == [(0, 3), (3, 3), (6, 2)] and _chunks(2, 5) == [(0, 2)]
+    assert M_MAX == 2 ** 31 - 1
+    Ms = [10, 20, 30, 40]
+    assert _split_for_sort([(0, 4)], Ms) == [(0, 4)]
+    big = [2 ** 30, 2 ** 30, 5, 2 ** 30]           # 2^30 + 2^30 > 2^31 - 1: the first two views cannot share a sort
+    assert _split_for_sort([(0, 4)], big) == [(0, 1), (1, 2), (3, 1)]
+    assert _split_for_sort([(0, 2), (2, 2)], big) == [(0, 1), (1, 1), (2, 2)]
+    import pytest
+    with pytest.raises(RuntimeError, match="2\\^31"):
+        _split_for_sort([(0, 1)], [2 ** 31])
