@@ -810,12 +810,9 @@ __global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
     float* s_quat = sm + 6 * G;    // [G,4]  -> dL_dquat slab
     float* s_gin = sm + 10 * G;    // [2][G, 8 + Cpad]  packed gradients of the current / next view
     const int gin_stride = (8 + Cpad) * G;
-    float* s_g3 = s_gin + 2 * gin_stride;                              // [G,3] dL_dxyz through the view direction
-    unsigned* s_list = reinterpret_cast<unsigned*>(s_g3 + 3 * G);      // [G]   Gaussians with a colour gradient
-    float* s_sh = s_g3 + 4 * G;                                        // [G, RS] coefficient rows, staged once
+    float* s_sh = s_gin + 2 * gin_stride;  // [G, RS] coefficient rows, staged once
     __shared__ float s_red[8 * 16];
     __shared__ unsigned long long s_bar[3];  // inputs | gradient buffer 0 | gradient buffer 1
-    __shared__ int s_cnt;
     const int rowf = Cs * D, RS = rp_pt_rs(rowf);
 
     const int tid = threadIdx.x;
@@ -855,6 +852,8 @@ __global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
     __syncthreads();
 
     const int t = tid;
+    const float4* my_sh = reinterpret_cast<const float4*>(s_sh + (size_t)t * RS);
+    float* my_out = dL_dshs + (g0 + t) * (long long)rowf;  // this Gaussian's dL_dshs row
     // geometry gradients, summed over the views in registers
     float dx = 0.f, dy = 0.f, dz = 0.f, dop = 0.f;
     float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -866,7 +865,6 @@ __global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
         float* s_grec = s_gin + (b & 1) * gin_stride;   // [G,8]
         float* s_gfeat = s_grec + 8 * G;                // [G,Cpad]
         const bool acc_b = accumulate || b > 0;
-        if (tid == 0) s_cnt = 0;
         if (full) {
             // every thread is past its reads of the other buffer (barrier at the end of the previous view)
             if (tid == 0 && b + 1 < views) prefetch(b + 1);
@@ -874,86 +872,59 @@ __global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
         } else {
             slab_load<RP_NT>(s_grec, grec, v0 * 8, rows * 8);
             slab_load<RP_NT>(s_gfeat, gfeat, v0 * Cpad, rows * Cpad);
+            __syncthreads();
         }
-        __syncthreads();
-
-        // ---- which Gaussians received a colour gradient in this view (29 % on BASELINE config #3): they are
-        // compacted so that the colour part below runs on dense warps instead of 9 of 32 lanes ----------------
-        bool vis = false, live = false;
-        if (t < rows) {
-            vis = tiles[v0 + t] > 0;
-            if (vis) {
-                const float* gf = s_gfeat + (size_t)t * Cpad;
-                for (int k = 0; k < Cs; ++k) live = live || (gf[k] != 0.f);
-            }
-            if (!live && !acc_b) {
-                // write mode: every row of dL_dshs must be produced (zeros for untouched Gaussians)
-                float4* row = reinterpret_cast<float4*>(dL_dshs + (g0 + t) * (long long)rowf);
-                for (int k = 0; k < rowf / 4; ++k) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        list_append(live, (unsigned)t, s_list, &s_cnt);
-        __syncthreads();
-
-        // ---- colour part: thread k takes the k-th live Gaussian ------------------------------------------------
-        if (tid < s_cnt) {
-            const int gl = (int)s_list[tid];
-            const float* gf = s_gfeat + (size_t)gl * Cpad;
-            const float4* my_sh = reinterpret_cast<const float4*>(s_sh + (size_t)gl * RS);
-            float* my_out = dL_dshs + (g0 + gl) * (long long)rowf;  // this Gaussian's dL_dshs row
-            const float rx = s_xyz[3 * gl] - cc.x, ry = s_xyz[3 * gl + 1] - cc.y, rz = s_xyz[3 * gl + 2] - cc.z;
-            const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
-            const float dirx = rx * inv, diry = ry * inv, dirz = rz * inv;
-            float bs[D], w[D];
-            sh_basis<DEG>(dirx, diry, dirz, bs, 1);
-#pragma unroll
-            for (int i = 0; i < D; ++i) w[i] = 0.f;
-            for (int ch = 0; ch < Cs; ++ch) {
-                float sv[D];
-                float acc = 0.f;
-#pragma unroll
-                for (int k = 0; k < D / 4; ++k) {
-                    const float4 x = my_sh[ch * (D / 4) + k];
-                    sv[4 * k] = x.x; sv[4 * k + 1] = x.y; sv[4 * k + 2] = x.z; sv[4 * k + 3] = x.w;
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i) acc = fmaf(sv[i], bs[i], acc);
-                // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
-                const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gf[ch];
-                float* op = my_out + ch * D;
-#pragma unroll
-                for (int k = 0; k < D / 4; ++k) {
-                    const float o0 = bs[4 * k] * dv, o1 = bs[4 * k + 1] * dv, o2 = bs[4 * k + 2] * dv, o3 = bs[4 * k + 3] * dv;
-                    if (acc_b) {
-                        if (dv != 0.f) red_add_v4(op + 4 * k, o0, o1, o2, o3);  // no read of the old row
-                    } else {
-                        *reinterpret_cast<float4*>(op + 4 * k) = make_float4(o0, o1, o2, o3);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i) w[i] = fmaf(sv[i], dv, w[i]);
-            }
-            float hx, hy, hz;  // dL_ddir
-            sh_basis_grad<DEG>(dirx, diry, dirz, w, 1, hx, hy, hz);
-            // dir = r / |r|  =>  dL_dr = (g - dir (dir . g)) / |r|
-            const float dt = dirx * hx + diry * hy + dirz * hz;
-            s_g3[3 * gl] = (hx - dirx * dt) * inv;
-            s_g3[3 * gl + 1] = (hy - diry * dt) * inv;
-            s_g3[3 * gl + 2] = (hz - dirz * dt) * inv;
-        }
-        __syncthreads();
-
-        // ---- geometry part: the thread that owns the Gaussian ----------------------------------------------------
         float cam[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) cam[i] = 0.f;
-        if (t < rows && vis) {
+        if (t < rows) {
+            const bool vis = tiles[v0 + t] > 0;
             const float px = s_xyz[3 * t], py = s_xyz[3 * t + 1], pz = s_xyz[3 * t + 2];
+            const float* gf = s_gfeat + (size_t)t * Cpad;
+            bool live = false;
+            if (vis)
+                for (int k = 0; k < Cs; ++k) live = live || (gf[k] != 0.f);
             float ax = 0.f, ay = 0.f, az = 0.f;
             if (live) {
-                ax = s_g3[3 * t];
-                ay = s_g3[3 * t + 1];
-                az = s_g3[3 * t + 2];
+                const float rx = px - cc.x, ry = py - cc.y, rz = pz - cc.z;
+                const float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+                const float dirx = rx * inv, diry = ry * inv, dirz = rz * inv;
+                float bs[D], w[D];
+                sh_basis<DEG>(dirx, diry, dirz, bs, 1);
+#pragma unroll
+                for (int i = 0; i < D; ++i) w[i] = 0.f;
+                for (int ch = 0; ch < Cs; ++ch) {
+                    float sv[D];
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D / 4; ++k) {
+                        const float4 x = my_sh[ch * (D / 4) + k];
+                        sv[4 * k] = x.x; sv[4 * k + 1] = x.y; sv[4 * k + 2] = x.z; sv[4 * k + 3] = x.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) acc = fmaf(sv[i], bs[i], acc);
+                    // same arithmetic as the forward pass -> same clamp decision (clamp_min passes x >= 0)
+                    const float dv = (clamp && !(acc + sh_bias >= 0.f)) ? 0.f : gf[ch];
+                    float* op = my_out + ch * D;
+#pragma unroll
+                    for (int k = 0; k < D / 4; ++k) {
+                        const float o0 = bs[4 * k] * dv, o1 = bs[4 * k + 1] * dv, o2 = bs[4 * k + 2] * dv, o3 = bs[4 * k + 3] * dv;
+                        if (acc_b) {
+                            if (dv != 0.f) red_add_v4(op + 4 * k, o0, o1, o2, o3);  // no read of the old row
+                        } else {
+                            *reinterpret_cast<float4*>(op + 4 * k) = make_float4(o0, o1, o2, o3);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i) w[i] = fmaf(sv[i], dv, w[i]);
+                }
+                float hx, hy, hz;  // dL_ddir
+                sh_basis_grad<DEG>(dirx, diry, dirz, w, 1, hx, hy, hz);
+                // dir = r / |r|  =>  dL_dr = (g - dir (dir . g)) / |r|
+                const float dt = dirx * hx + diry * hy + dirz * hz;
+                ax = (hx - dirx * dt) * inv;
+                ay = (hy - diry * dt) * inv;
+                az = (hz - dirz * dt) * inv;
                 if (CAM) {
                     // r = p - centre, centre = -R^T t  =>  dL_dR[i][j] += dL_dr[j] t[i], dL_dt[i] += R[i][:] . dL_dr
 #pragma unroll
@@ -965,39 +936,43 @@ __global__ void __launch_bounds__(RP_NT, 2) render_pre_bwd_pt_kernel(
                         cam[4 + 4 * i + 3] += c.e[4 * i] * ax + c.e[4 * i + 1] * ay + c.e[4 * i + 2] * az;
                     }
                 }
+            } else if (!acc_b) {
+                // write mode: every row of dL_dshs must be produced (zeros for untouched Gaussians)
+                for (int k = 0; k < rowf / 4; ++k) reinterpret_cast<float4*>(my_out)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float* gf = s_gfeat + (size_t)t * Cpad;
-            const float4 ga = reinterpret_cast<const float4*>(s_grec)[2 * t];      // dL_duv, dL_dconic.xy
-            const float4 gb = reinterpret_cast<const float4*>(s_grec)[2 * t + 1];  // dL_dconic.z, dL_dopacity
-            dop += gb.y;
-            const float gd = with_depth ? gf[Cs] : 0.f;
-            float bx, by, bz;
-            project_bwd<CAM>(c, px, py, pz, ga.x, ga.y, gd, bx, by, bz, cam);
-            ax += bx;
-            ay += by;
-            az += bz;
-            const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
-            const float sx = s_scale[3 * t], sy = s_scale[3 * t + 1], sz = s_scale[3 * t + 2];
-            float cv[6], dcv[6], ex, ey, ez;
-            cov3d_fwd(sx, sy, sz, q.x, q.y, q.z, q.w, cv);
-            if (ewa_bwd<CAM>(c, px, py, pz, cv, ga.z, ga.w, gb.x, ex, ey, ez, dcv, cam)) {
-                ax += ex;
-                ay += ey;
-                az += ez;
-                float vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f};
-                cov3d_bwd(sx, sy, sz, q.x, q.y, q.z, q.w, dcv, vs, vq);
+            if (vis) {
+                const float4 ga = reinterpret_cast<const float4*>(s_grec)[2 * t];      // dL_duv, dL_dconic.xy
+                const float4 gb = reinterpret_cast<const float4*>(s_grec)[2 * t + 1];  // dL_dconic.z, dL_dopacity
+                dop += gb.y;
+                const float gd = with_depth ? gf[Cs] : 0.f;
+                float bx, by, bz;
+                project_bwd<CAM>(c, px, py, pz, ga.x, ga.y, gd, bx, by, bz, cam);
+                ax += bx;
+                ay += by;
+                az += bz;
+                const float4 q = reinterpret_cast<const float4*>(s_quat)[t];
+                const float sx = s_scale[3 * t], sy = s_scale[3 * t + 1], sz = s_scale[3 * t + 2];
+                float cv[6], dcv[6], ex, ey, ez;
+                cov3d_fwd(sx, sy, sz, q.x, q.y, q.z, q.w, cv);
+                if (ewa_bwd<CAM>(c, px, py, pz, cv, ga.z, ga.w, gb.x, ex, ey, ez, dcv, cam)) {
+                    ax += ex;
+                    ay += ey;
+                    az += ez;
+                    float vs[3] = {0.f, 0.f, 0.f}, vq[4] = {0.f, 0.f, 0.f, 0.f};
+                    cov3d_bwd(sx, sy, sz, q.x, q.y, q.z, q.w, dcv, vs, vq);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) ds[i] += vs[i];
+                    for (int i = 0; i < 3; ++i) ds[i] += vs[i];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dq[i] += vq[i];
+                    for (int i = 0; i < 4; ++i) dq[i] += vq[i];
+                }
+                dx += ax;
+                dy += ay;
+                dz += az;
             }
-            dx += ax;
-            dy += ay;
-            dz += az;
         }
         if (CAM) cam_reduce_atomic<RP_NT>(cam, dL_dintr ? dL_dintr + 4 * b : nullptr,
                                           dL_dextr ? dL_dextr + (size_t)estride * b : nullptr, s_red);
-        __syncthreads();  // this view's gradient buffer, list and direction gradients may now be overwritten
+        __syncthreads();  // this view's gradient buffer may now be overwritten
     }
 
     if (t < rows) {
@@ -1048,7 +1023,7 @@ static size_t rp_pt_smem_fwd(int Cs, int D, int Cpad) {
     return ((size_t)rp_pt_fwd_io(Cpad) * RP_NT + (size_t)rp_pt_rs(Cs * D) * RP_NT) * sizeof(float);
 }
 static size_t rp_pt_smem_bwd(int Cs, int D, int Cpad) {
-    return ((size_t)14 * RP_NT + 2 * (size_t)(8 + Cpad) * RP_NT + (size_t)rp_pt_rs(Cs * D) * RP_NT) * sizeof(float);
+    return ((size_t)10 * RP_NT + 2 * (size_t)(8 + Cpad) * RP_NT + (size_t)rp_pt_rs(Cs * D) * RP_NT) * sizeof(float);
 }
 // PT path: degree 1 or 3, rows of at most RP_PT_MAX_ROW floats, 16-byte aligned rows; MSB_RP_PT=0 disables (A/B)
 static bool rp_use_pt(int deg, int Cs) {
