@@ -314,12 +314,15 @@ def run_gpu(args, api, impl):
         loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         copy_stream = torch.cuda.Stream(device=dev)
         g_dev = torch.empty_like(G)
-        # one untimed e2e step: the first one allocates the copy stream's buffers and the pinned staging of the loss
-        with torch.cuda.stream(copy_stream):
-            g_dev.copy_(G_host, non_blocking=True)
-            g_ev = copy_stream.record_event()
-        loss_host.copy_(step(intr_h.to(dev, non_blocking=True), extr_h.to(dev, non_blocking=True),
-                             cent_h.to(dev, non_blocking=True), Staged(g_dev, g_ev)).reshape(1), non_blocking=True)
+        # untimed e2e steps: the first one allocates the copy stream's buffers and the pinned staging of the loss; with
+        # N > 1 the allocator needs a few steps of this loop's own allocation pattern to settle (see the warm-up above)
+        for _ in range(3 if world > 1 else 1):
+            with torch.cuda.stream(copy_stream):
+                g_dev.copy_(G_host, non_blocking=True)
+                g_ev = copy_stream.record_event()
+            loss_host.copy_(step(intr_h.to(dev, non_blocking=True), extr_h.to(dev, non_blocking=True),
+                                 cent_h.to(dev, non_blocking=True), Staged(g_dev, g_ev)).reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         barrier_sync(world)
         e0.record()
         # The 33 MB cotangent is copied every step on a copy stream into a reused device buffer, under the
@@ -339,9 +342,11 @@ def run_gpu(args, api, impl):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if args.trace and rank == 0:  # CPU + GPU timeline of three e2e steps (diagnostic; not a measurement)
+        if args.trace:  # CPU + GPU timeline of three e2e steps of rank 0 (diagnostic; every rank runs the steps)
+            import contextlib
             from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            cm = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) if rank == 0 else contextlib.nullcontext()
+            with cm as prof:
                 for _ in range(3):
                     with torch.cuda.stream(copy_stream):
                         g_dev.copy_(G_host, non_blocking=True)
@@ -351,7 +356,9 @@ def run_gpu(args, api, impl):
                     tot = step(*ins)
                     loss_host.copy_(tot.reshape(1), non_blocking=True)
                     torch.cuda.current_stream().synchronize()
-            prof.export_chrome_trace(args.trace)
+            if rank == 0:
+                prof.export_chrome_trace(args.trace)
+            barrier_sync(world)
         n = world * V * args.steps
         return ms / args.steps, n / (ms / 1e3), n / (float(t[0]) / 1e3), launches, timing, (t0, t1)
 
