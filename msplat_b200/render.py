@@ -418,6 +418,10 @@ class _RenderSHViews(torch.autograd.Function):
                 for w in works:
                     if w is not None and hasattr(w, "wait"):
                         w.wait()
+                # NCCL's work objects keep the reduced tensors referenced for a while; autograd's AccumulateGrad then
+                # cannot adopt them as .grad and clones them (708 MB of device copies per step at 3M Gaussians).
+                # Fresh aliases have a single owner and are adopted as they are.
+                dxyz, dscale, dquat, dop, dshs = (t.view_as(t) for t in outs)
             gr = grec[:, :P]
             if ctx.has_ndc:  # screen-space gradient hook: dL_duv of view b is columns 0:2 of its packed record
                 dndc = gr[:, :, :2] * torch.tensor([0.5 * W, 0.5 * H], dtype=f32, device=dev)
