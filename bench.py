@@ -739,7 +739,7 @@ def main():
     ap.add_argument("--api", default="fused", choices=["fused", "steps"],
                     help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
     ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
-    ap.add_argument("--grad-chunks", type=int, default=3,
+    ap.add_argument("--grad-chunks", type=int, default=4,
                     help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels")
     ap.add_argument("--view-chunk", type=int, default=0, help="views per batched launch (0 = all views of the rank)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 5],

@@ -98,7 +98,7 @@ def rasterization_sh(
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 3, ndc: Tensor = None,
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 4, ndc: Tensor = None,
     return_aux: bool = False, view_chunk: int = None, stats: dict = None,
 ):
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
