@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x --timeout=900 -p no:cacheprovider -k "grad_sync or ndc_hook" 2>&1 | tail -2
-bash tools/gpu_multi.sh r2s "2|--steps 8 --grad-chunks 3" "2|--steps 8 --grad-chunks 4" "2|--steps 8 --grad-chunks 6" "2|--steps 8 --grad-chunks 2"
+bash tools/gpu_multi.sh r2f8 "8|--steps 8" "4|--steps 8" "8|--config 5 --steps 4"
