@@ -9,7 +9,7 @@ over hand-written CUDA kernels reached through the C ABI in ``include/msplat_b20
 import torch
 from torch import Tensor
 
-from . import _lib
+from . import _lib, optim  # noqa: F401  (msplat_b200.optim.FusedAdam)
 from ._lib import as_f32, ptr
 from .alpha_blending import _blend_backward, _blend_forward, alpha_blending
 from .compute_cov3d import compute_cov3d
