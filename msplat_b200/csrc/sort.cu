@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int Pv /*Gaussians
                                                        const int* __restrict__ radius,
                                                        const int* __restrict__ tiles, int gx, int gy,
                                                        unsigned int* __restrict__ dkeys, int* __restrict__ dvals,
-                                                       int4* __restrict__ rect /*[P] {x0, y0, w, n} of the emitters*/,
+                                                       int4* __restrict__ rect /*[Pc] {x0 | w << 16, y0, n, id} of the emitters, compact*/,
                                                        unsigned int* __restrict__ hist /*[4][256]*/,
                                                        unsigned int* __restrict__ zcount,
                                                        unsigned int* __restrict__ status /*[gridDim.x]*/,
@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(KG_NT) keygen_kernel(int P, int Pv /*Gaussians
             if (n > 0) {
                 const unsigned int o = pos + __popc(em & lt_mask);
                 dkeys[o] = dk[r];
-                dvals[o] = (int)i;
-                rect[i] = make_int4(x0, y0 + (int)(i / Pv) * gy, w, n);
+                dvals[o] = (int)o;  // the depth passes carry the emitter's compact slot; its id sits in the record
+                rect[o] = make_int4(x0 | (w << 16), y0 + (int)(i / Pv) * gy, n, (int)i);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((dk[r] >> (8 * p)) & 255u)], 1u);
             }
@@ -605,9 +605,10 @@ __device__ __forceinline__ void peer_bit(unsigned d, unsigned& m) {
 // IPT: keys per thread (16).  A/B on BASELINE config #3 (profiles/r1_ab_experiments.md): 8 keys per thread
 // at 6 CTAs/SM and look-back windows of 16 / 32 were not faster for the L2-resident depth passes;
 // what helped them was the single-lane wait below (gate_ns).
-// GATHER (last depth pass): while scattering, the kernel also fetches the tile rectangle of every Gaussian
-// (rect[id], the pipeline's one random gather) and writes it, with the id, at the Gaussian's depth-order position:
-// rsorted[pos] = {x0 | w << 16, y0, n, id} -- the offset scan and the duplication then stream sequentially.
+// GATHER (last depth pass): while scattering, the kernel fetches the 16-byte record {x0 | w << 16, y0, n, id} that
+// keygen wrote at the emitter's compact slot (the value the depth passes carry; the pipeline's one random gather, over
+// a dense array) and writes it at the Gaussian's depth-order position -- the offset scan and the duplication then
+// stream sequentially.
 template <bool DEVN, int LB, int NB, int IPT, bool GATHER = false>
 __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int N, const unsigned int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ kin,
                                                             const int* __restrict__ vin,
@@ -767,9 +768,7 @@ __global__ void __launch_bounds__(RS_NT, IPT >= 16 ? 4 : 6) onesweep_kernel(int 
         const unsigned d = k & 255u;
         const long long g = (long long)sm.gadj[d] + j;
         if (GATHER) {
-            const int id = sm.vals[j];
-            const int4 r = rect[id];
-            rsorted[g] = make_int4(r.x | (r.z << 16), r.y, r.w, id);
+            rsorted[g] = rect[sm.vals[j]];  // 16-byte record of the emitter whose compact slot the passes carried
         } else {
             kout[g] = __funnelshift_l(k, k, shift);
             vout[g] = sm.vals[j];
