@@ -651,6 +651,14 @@ __device__ __forceinline__ void pt_stage_rows(float* __restrict__ s_sh, const fl
 // overlay them
 __host__ __device__ constexpr int rp_pt_fwd_io(int Cpad) { return (10 + Cpad) > 11 ? (10 + Cpad) : 11; }
 
+// Thread 0 moves the CTA's tile count of one view into the per-view total and re-arms the counter.  An atomic exchange
+// (not a plain load + store): the compiler may not hoist it to the other threads, so no thread but 0 ever touches the
+// word between the warps' atomicAdds of two views (racecheck-clean; a speculated plain load was flagged).
+__device__ __forceinline__ void pt_drain_tiles(unsigned* s_tsum, unsigned long long* total_tiles, int b) {
+    const unsigned s = atomicExch(s_tsum, 0u);
+    if (total_tiles != nullptr && s) atomicAdd(total_tiles + b, (unsigned long long)s);
+}
+
 template <int DEG>
 __global__ void __launch_bounds__(RP_NT, 3) render_pre_fwd_pt_kernel(
     int P, int Cs, int Cpad, int with_depth, int views, long long vstride, const float* __restrict__ xyz,
@@ -681,6 +689,7 @@ __global__ void __launch_bounds__(RP_NT, 3) render_pre_fwd_pt_kernel(
     const int gx = (W + MSB_TILE - 1) / MSB_TILE, gy = (H + MSB_TILE - 1) / MSB_TILE;
     const bool full = rows == G;
     if (tid == 0 && full) mbar_init(&s_bar, 1);
+    if (tid == 0) s_tsum = 0;
     __syncthreads();
     pt_stage_rows(s_sh, shs, g0, rows, rowf, RS);
     if (full) {
@@ -717,8 +726,7 @@ __global__ void __launch_bounds__(RP_NT, 3) render_pre_fwd_pt_kernel(
         const Cam c = load_cam(intr + 4 * b, extr + (size_t)estride * b);
         const CamCenter cc = cam_center(c);
         const long long v0 = (long long)b * vstride + g0;  // first output row of this block in view b
-        if (tid == 0) s_tsum = 0;
-        __syncthreads();  // also: the previous view's bulk stores have read the output slabs (thread 0 waited)
+        __syncthreads();  // the previous view's stores have read the output slabs (thread 0 waited); s_tsum drained
 
         float u = 0.f, v = 0.f, d = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, hx = 0.f, hy = 0.f;
         int rad = 0, til = 0;
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(RP_NT, 3) render_pre_fwd_pt_kernel(
             fence_async_smem();  // this thread's slab writes -> visible to the bulk stores below
             __syncthreads();
             if (tid == 0) {
-                if (total_tiles != nullptr && s_tsum) atomicAdd(total_tiles + b, (unsigned long long)s_tsum);
+                pt_drain_tiles(&s_tsum, total_tiles, b);
                 bulk_s2g(rec + v0 * 8, s_rec, 8 * G * sizeof(float));
                 bulk_s2g(uv + v0 * 2, s_uv, 2 * G * sizeof(float));
                 bulk_s2g(featp + v0 * Cpad, s_feat, (unsigned)((size_t)Cpad * G * sizeof(float)));
@@ -784,7 +792,7 @@ __global__ void __launch_bounds__(RP_NT, 3) render_pre_fwd_pt_kernel(
             }
         } else {
             __syncthreads();
-            if (tid == 0 && total_tiles != nullptr && s_tsum) atomicAdd(total_tiles + b, (unsigned long long)s_tsum);
+            if (tid == 0) pt_drain_tiles(&s_tsum, total_tiles, b);
             slab_store<RP_NT>(rec, s_rec, v0 * 8, rows * 8);
             slab_store<RP_NT>(uv, s_uv, v0 * 2, rows * 2);
             slab_store<RP_NT>(featp, s_feat, v0 * Cpad, rows * Cpad);
