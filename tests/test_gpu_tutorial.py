@@ -56,18 +56,60 @@ def test_gs2d_loss_falls():
 
 
 def test_gs2d_tracks_reference(ref_msplat):
-    """120 Adam iterations on the tutorial's target: our loss curve (fused Adam) stays as close to the reference's
-    as a second run of the reference does (x4), or within 1e-3 relative where the reference repeats itself."""
+    """The tutorial's optimisation against the unmodified reference build, 120 Adam iterations on its target.
+
+    The loop is chaotic: both libraries accumulate gradients with float atomics (ulp-level run-to-run noise, measured
+    below), Adam turns a sign flip of a tiny gradient into an lr-sized step, and the rasteriser has discrete events
+    (a Gaussian gaining a tile, an alpha crossing 1/255).  Two runs of ONE library separate at a random iteration
+    (7..60 observed) and then differ by up to ~10 % in loss (profiles/r2_gs2d_acceptance_20k.json), so a free-running
+    curve comparison cannot be tight.  What can be: (1) teacher forcing -- along the reference's own trajectory, on the
+    reference's parameters of iterations 0, 5, 15, 30, 60 and 119, our image equals the reference's and our gradients
+    are within 1e-3 |g| + K_NOISE x the reference's measured run-to-run spread; (2) the free-running curves coincide
+    before the chaos sets in and their 10-iteration means stay within 10 % after it."""
     import msplat_b200
+    from test_gpu_parity import compare_grads
     t = _tutorial()
     target = t.load_target(None, 512).cuda()
-    iters = 120
-    a = t.fit(msplat_b200, target, points=20000, iters=iters, quiet=True, optimizer="fused")
-    b1 = t.fit(ref_msplat, target, points=20000, iters=iters, quiet=True)
-    b2 = t.fit(ref_msplat, target, points=20000, iters=iters, quiet=True)
-    spread = 0.0
+    iters, points = 120, 20000
+    _, H, W = target.shape
+    intr, extr = t.camera(W, H, target.device)
+    loss_fn = torch.nn.SmoothL1Loss()
+
+    # (1) teacher forcing along the reference's trajectory
+    params = t.make_parameters(points, target.device, torch.Generator().manual_seed(123))
+    opt = torch.optim.Adam(list(params.values()), lr=0.01)
+    names = list(params.keys())
+
+    def grads_of(api):
+        def run():
+            leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+            image = api.rasterization(*t.activated(leaves), intr, extr, W, H, 1.0)
+            loss_fn(image, target).backward()
+            return [leaves[k].grad for k in names] + [image.detach()]
+        return run
+
+    for it in range(iters):
+        if it in (0, 5, 15, 30, 60, iters - 1):
+            ours, ref = grads_of(msplat_b200), grads_of(ref_msplat)
+            assert torch.equal(ours()[-1], ref()[-1]), f"iteration {it}: images differ on the reference's parameters"
+            # 5 reference runs for the spread; a handful of strongly cancelling elements (|g| < 1e-4 max|g|) may
+            # exceed K_NOISE x the largest spread seen in so few runs
+            compare_grads(lambda: ours()[:-1], lambda: ref()[:-1], names, f"gs_2d teacher-forced it={it}", n=4,
+                          min_frac=1.0 - 1e-4)
+        image = ref_msplat.rasterization(*t.activated(params), intr, extr, W, H, 1.0)
+        loss_fn(image, target).backward()
+        opt.step()
+        opt.zero_grad()
+
+    # (2) free-running curves
+    a = t.fit(msplat_b200, target, points=points, iters=iters, quiet=True, optimizer="fused")
+    b = t.fit(ref_msplat, target, points=points, iters=iters, quiet=True)
+    for k in range(6):  # before the chaos: the curves coincide
+        assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]), f"iteration {k}: {a[k]} vs reference {b[k]}"
+    # after it: single iterations of two runs of one library differ by up to 11 % (Adam overshoots show up as spikes
+    # one iteration apart), their 10-iteration means by < 3 % (3 + 3 runs, B200); bound the means at 10 %
+    mean10 = lambda x, k: sum(x[max(0, k - 9):k + 1]) / len(x[max(0, k - 9):k + 1])
     for k in range(iters):
-        spread = max(spread, abs(b1[k] - b2[k]))  # how far two runs of the reference have drifted apart by now
-        assert abs(a[k] - b1[k]) <= 1e-3 * abs(b1[k]) + 4.0 * spread, \
-            f"iteration {k}: {a[k]} vs reference {b1[k]} (reference vs itself: {spread:.3e})"
+        ma, mb = mean10(a, k), mean10(b, k)
+        assert abs(ma - mb) <= 0.10 * mb, f"iteration {k}: 10-iteration mean {ma} vs reference {mb}"
     assert a[-1] < 0.7 * a[0]
