@@ -262,8 +262,11 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
                                                  int foff, int geom_grads) {
     __syncwarp();
     const int g = lane & (BW_GQ - 1), h = lane >> 4;
-    float m0 = 0.f, mxy = 0.f;
-    f32x2 m1 = pk2(0.f, 0.f), m2 = pk2(0.f, 0.f);  // (sum X dx, sum X dy), (sum X dx^2, sum X dy^2)
+    // Raw moments of X over this half's 2 x 8 pixels about the block's column origin, one set per pixel row:
+    // a = sum X, ax = sum X x, axx = sum X x^2 with x = 0..7 a compile-time constant of the unrolled loop (FFMA with
+    // an immediate; no per-pixel dx / dy arithmetic).  They are shifted to the Gaussian's centre once per group below.
+    float a0 = 0.f, ax0 = 0.f, axx0 = 0.f, a1 = 0.f, ax1 = 0.f, axx1 = 0.f;
+    float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f;
     f32x2 fs[CH / 2];
 #pragma unroll
     for (int k = 0; k < CH / 2; ++k) fs[k] = pk2(0.f, 0.f);
@@ -275,24 +278,21 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
         const float4 r1 = st.rec[2 * j + 1];
         id = sid[j];
         cx = r0.z; cy = r0.w; cz = r1.x; op = r1.y;
-        const float ux = r0.x - wx0;                       // dx of pixel column i: ux - i
-        const float dy0 = r0.y - (wy0 + (float)(2 * h));   // rows 2h and 2h+1 of the 8x4 block
-        const float dy1 = dy0 - 1.0f;
         const float2* row = xw + g * BW_PS + h * 16;
         const float4* dp = reinterpret_cast<const float4*>(dpw + h * 16 * CH);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const float2 v = row[q];
-            const float dx = ux - (float)(q & 7);
-            const float dy = (q >> 3) ? dy1 : dy0;
-            const f32x2 d2 = pk2(dx, dy);
-            const f32x2 xd = mul2(pk2(v.x, v.x), d2);  // (X dx, X dy)
-            m1 = add2(m1, xd);
-            m2 = fma2(xd, d2, m2);
-            float xdx, xdy;
-            upk2(xd, xdx, xdy);
-            mxy = fmaf(xdx, dy, mxy);
-            m0 += v.x;
+            const float x = (float)(q & 7);
+            if (q < 8) {
+                a0 += v.x;
+                ax0 = fmaf(v.x, x, ax0);
+                axx0 = fmaf(v.x, x * x, axx0);
+            } else {
+                a1 += v.x;
+                ax1 = fmaf(v.x, x, ax1);
+                axx1 = fmaf(v.x, x * x, axx1);
+            }
             const f32x2 w2 = pk2(v.y, v.y);
 #pragma unroll
             for (int k = 0; k < CH; k += 4) {
@@ -301,11 +301,19 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
                 fs[k / 2 + 1] = fma2(w2, pk2(d.z, d.w), fs[k / 2 + 1]);
             }
         }
+        // dx = ux - x, dy = dy0 (row 2h) or dy1 (row 2h + 1)
+        const float ux = r0.x - wx0;
+        const float dy0 = r0.y - (wy0 + (float)(2 * h));
+        const float dy1 = dy0 - 1.0f;
+        const float s0 = a0 + a1, sx = ax0 + ax1, sxx = axx0 + axx1;
+        m0 = s0;
+        mx = fmaf(ux, s0, -sx);                             // sum X dx
+        mxx = fmaf(ux, fmaf(ux, s0, -2.0f * sx), sxx);      // sum X dx^2
+        my = fmaf(dy0, a0, dy1 * a1);                       // sum X dy
+        myy = fmaf(dy0 * dy0, a0, dy1 * dy1 * a1);          // sum X dy^2
+        mxy = fmaf(dy0, fmaf(ux, a0, -ax0), dy1 * fmaf(ux, a1, -ax1));  // sum X dx dy
     }
     // combine the two pixel halves (every lane takes part; idle lanes hold zeros)
-    float mx, my, mxx, myy;
-    upk2(m1, mx, my);
-    upk2(m2, mxx, myy);
     m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
     mx += __shfl_xor_sync(0xffffffffu, mx, 16);
     my += __shfl_xor_sync(0xffffffffu, my, 16);
