@@ -247,16 +247,15 @@ struct Bwd3 {
     static constexpr size_t STAGE_BYTES = 2 * sizeof(Stage<CH, B>);
     static constexpr size_t XW_BYTES = (size_t)(BL_NT / 32) * BW_GQ * BW_PS * sizeof(float2);
     static constexpr size_t DPIX_BYTES = (size_t)BL_NT * CH * sizeof(float);
-    static constexpr size_t Q_BYTES = (size_t)(BL_NT / 32) * BW_GQ * sizeof(int);
     static constexpr int HL_STRIDE = B + 2;  // hit list of one warp: batch slots that pass the footprint test (+ pad)
     static constexpr size_t HL_BYTES = (size_t)(BL_NT / 32) * HL_STRIDE * sizeof(unsigned short);
-    static constexpr size_t SMEM = STAGE_BYTES + XW_BYTES + DPIX_BYTES + Q_BYTES + HL_BYTES;
+    static constexpr size_t SMEM = STAGE_BYTES + XW_BYTES + DPIX_BYTES + HL_BYTES;
 };
 
 // phase 2 for the first n (<= BW_GQ) parked visits of this warp
 template <int CH, int B>
 __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH, B>& st, const int* __restrict__ sid,
-                                                 const int* __restrict__ qw, const float2* __restrict__ xw,
+                                                 const float2* __restrict__ xw,
                                                  const float* __restrict__ dpw, float wx0, float wy0,
                                                  float* __restrict__ grec, float* __restrict__ gfeat, int fstride,
                                                  int foff, int geom_grads) {
@@ -273,7 +272,7 @@ __device__ __forceinline__ void bwd_reduce_group(int n, int lane, const Stage<CH
     float cx = 0.f, cy = 0.f, cz = 0.f, op = 0.f;
     int id = 0;
     if (g < n) {
-        const int j = qw[g];
+        const int j = __float_as_int(xw[g * BW_PS + 32].x);  // the row's pad cell holds the staged slot
         const float4 r0 = st.rec[2 * j];
         const float4 r1 = st.rec[2 * j + 1];
         id = sid[j];
@@ -362,9 +361,8 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
     Stage<CH, B>* stages = reinterpret_cast<Stage<CH, B>*>(bl_raw);
     float2* s_xw = reinterpret_cast<float2*>(bl_raw + L::STAGE_BYTES);
     float* s_dpix = reinterpret_cast<float*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES);
-    int* s_q = reinterpret_cast<int*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES + L::DPIX_BYTES);
     unsigned short* s_hl =
-        reinterpret_cast<unsigned short*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES + L::DPIX_BYTES + L::Q_BYTES);
+        reinterpret_cast<unsigned short*>(bl_raw + L::STAGE_BYTES + L::XW_BYTES + L::DPIX_BYTES);
     __shared__ int s_id[2 * B];  // [2][B] Gaussian ids of the staged slots
     __shared__ int s_max[BL_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -390,7 +388,7 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
     if (lane == 0) s_max[warp] = wmax;
 
     const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
+    float Tn = -T_final;  // the replay keeps the transmittance negated (see replay)
     f32x2 dpix2[CH / 2], S2[CH / 2];  // cotangent and suffix colour, two channels per 64-bit register pair
     float bgdot = 0.f;
     float* dpw = s_dpix + warp * 32 * CH;  // this warp's cotangents, [pixel][channel]
@@ -418,9 +416,8 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
     const float nbg = -T_final * bgdot;  // background term of dL_dalpha, still to be divided by (1 - alpha)
 
     float2* xw = s_xw + warp * (BW_GQ * BW_PS);
-    int* qw = s_q + warp * BW_GQ;
     float2* xw_wr = xw + lane;  // this lane's cell in the row of the next parked visit
-    int* qw_wr = qw;            // its slot index (warp-uniform pointer; every lane stores the same value)
+    // a parked visit occupies one row; lane 0 also stores the visit's staged slot in the row's pad cell (column 32)
     int cnt = 0;                // parked visits (warp-uniform)
 
     // batches walk the list back to front: batch b, slot j <-> list position maxc-1-(b*256+j)
@@ -487,34 +484,36 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
                 const float alpha = valid ? araw : 0.0f;
                 const float G = valid ? Graw : 0.0f;
                 const float rinv = rcp_approx(1.0f - alpha);  // == 1 for a failing pair
-                T = T * rinv;                                  // :205
-                const float wgt = alpha * T;
+                Tn = Tn * rinv;                                // :205, kept negated: Tn = -T
+                const float wgt = fmul(-alpha, Tn);            // alpha T
                 // channel math on packed pairs (FFMA2/FMUL2): per pair of channels
                 //   e = f T - S / (1 - alpha);  dL_dalpha += e . dpix;  S += f alpha T
-                const f32x2 T2 = pk2(T, T), W2 = pk2(wgt, wgt), NR2 = pk2(-rinv, -rinv);
-                f32x2 dacc = pk2(nbg * rinv, 0.f);             // :222-229 (background term)
+                // computed as -e = S rinv + f Tn so that no operand has to be negated (the packed ops take no
+                // negation modifier); the sign returns for free in the scalar FFMA that adds the background term
+                const f32x2 TN2 = pk2(Tn, Tn), W2 = pk2(wgt, wgt), R2 = pk2(rinv, rinv);
+                f32x2 dacc;
 #pragma unroll
                 for (int k = 0; k < CH; k += 4) {
                     const float4 fv = *reinterpret_cast<const float4*>(&st.feat[j * CH + k]);
                     const f32x2 fa = pk2(fv.x, fv.y), fb = pk2(fv.z, fv.w);
-                    const f32x2 ea = fma2(S2[k / 2], NR2, mul2(fa, T2));           // :213-217
-                    const f32x2 eb = fma2(S2[k / 2 + 1], NR2, mul2(fb, T2));
-                    dacc = fma2(ea, dpix2[k / 2], dacc);
+                    const f32x2 ea = fma2(fa, TN2, mul2(S2[k / 2], R2));           // :213-217
+                    const f32x2 eb = fma2(fb, TN2, mul2(S2[k / 2 + 1], R2));
+                    dacc = k == 0 ? mul2(ea, dpix2[0]) : fma2(ea, dpix2[k / 2], dacc);
                     dacc = fma2(eb, dpix2[k / 2 + 1], dacc);
                     S2[k / 2] = fma2(fa, W2, S2[k / 2]);
                     S2[k / 2 + 1] = fma2(fb, W2, S2[k / 2 + 1]);
                 }
                 float dlo, dhi;
                 upk2(dacc, dlo, dhi);
-                *xw_wr = make_float2(G * (dlo + dhi), wgt);  // (X, w) of this pair
+                // X = G dL/dalpha, dL/dalpha = e . dpix + nbg / (1 - alpha)   (:222-229: background term)
+                *xw_wr = make_float2(G * fmaf(nbg, rinv, -(dlo + dhi)), wgt);  // (X, w) of this pair
+                if (lane == 0) xw_wr[32].x = __int_as_float(j);
                 xw_wr += BW_PS;
-                *qw_wr++ = j;
                 if (++cnt == BW_GQ) {
-                    bwd_reduce_group<CH, B>(BW_GQ, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
+                    bwd_reduce_group<CH, B>(BW_GQ, lane, st, sid, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff,
                                             geom_grads);
                     cnt = 0;
                     xw_wr = xw + lane;
-                    qw_wr = qw;
                 }
             };
             // Two hits per iteration: their alpha evaluations (LDS -> 7 dependent FP32 ops -> MUFU.EX2 -> min ->
@@ -538,10 +537,9 @@ __global__ void __launch_bounds__(BL_NT, MINB) blend_bwd_kernel(const float4* __
             }
         }
         if (cnt > 0) {  // the stage buffer is recycled after this batch
-            bwd_reduce_group<CH, B>(cnt, lane, st, sid, qw, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff, geom_grads);
+            bwd_reduce_group<CH, B>(cnt, lane, st, sid, xw, dpw, wx0, wy0, grec, gfeat, fstride, foff, geom_grads);
             cnt = 0;
             xw_wr = xw + lane;
-            qw_wr = qw;
         }
     }
     cp_async_wait<0>();
