@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
         }
         const Stage<CH>& st = stages[b & 1];
         const int cnt = min(BL_BATCH, n - b * BL_BATCH);
-        const int base1 = b * BL_BATCH + 1;
         if (__all_sync(0xffffffffu, done)) continue;
+        int lastj = 0;  // 1 + slot of this pixel's last blended entry within the batch (0: none yet)
         for (int k0 = 0; k0 < cnt; k0 += 32) {
             bool hit = false;
             if (k0 + lane < cnt) {
@@ -195,11 +195,12 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
                     F[k + 3] = ffma(T, p3, F[k + 3]);
                 }
                 T = blend ? nT : T;
-                last = blend ? base1 + j : last;
+                lastj = blend ? j + 1 : lastj;
                 if (COUNT) nblend += blend ? 1 : 0;
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
+        if (lastj) last = b * BL_BATCH + lastj;  // list position + 1 (alpha_blending.cu: n_contrib)
     }
     cp_async_wait<0>();
     if (inside) {
