@@ -385,7 +385,8 @@ def run_gpu(args, api, impl):
                    "baseline_config": 5 if cfg5 else 3,
                    "gaussians": P, "width": W, "height": H, "sh_degree": SH_DEG, "channels": C,
                    "views_per_rank_per_step": V, "parallelism": f"view-dp{world}", "api": api_note,
-                   "view_chunk": args.view_chunk, "grad_chunks": args.grad_chunks,
+                   "view_chunk": args.view_chunk,
+                   "grad_chunks": args.grad_chunks or (0 if world == 1 else 4 if world <= 2 else 2),
                    "cache": "inputs (~0.7 GB of parameters per render) exceed the 126 MB L2; no explicit flush"},
         "impl": impl, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "renders/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -739,8 +740,10 @@ def main():
     ap.add_argument("--api", default="fused", choices=["fused", "steps"],
                     help="--impl ours only: fused view-batch Function (default) or the reference-style steps API")
     ap.add_argument("--no-steps-api", action="store_true", help="skip the secondary steps-API measurement")
-    ap.add_argument("--grad-chunks", type=int, default=4,
-                    help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels")
+    ap.add_argument("--grad-chunks", type=int, default=0,
+                    help="N > 1: Gaussian slabs of the backward whose all-reduce overlaps the next slab's kernels "
+                         "; 0 = the library's default (4 slabs for 2 ranks, 2 beyond; ms per step at N = 8 / 4 with 1, 2, 3, 4 slabs: "
+                         "17.65, 17.23, -, 17.68 / -, 17.09, 17.60, 17.55)")
     ap.add_argument("--view-chunk", type=int, default=0, help="views per batched launch (0 = all views of the rank)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 5],
                     help="BASELINE config: 3 = headline (default), 5 = 6M Gaussians, 4K, 64 cameras strong-scaled over N")

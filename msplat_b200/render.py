@@ -98,7 +98,7 @@ def rasterization_sh(
 def rasterization_sh_views(
     xyz: Tensor, scale: Tensor, rotate: Tensor, opacity: Tensor, shs: Tensor, intrs: Tensor, extrs: Tensor,
     W: int, H: int, bg: float, *, sh_bias: float = 0.5, clamp: bool = True, with_depth: bool = False,
-    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = 4, ndc: Tensor = None,
+    nearest: float = 0.0, extent: float = 1.3, grad_sync=None, grad_chunks: int = None, ndc: Tensor = None,
     return_aux: bool = False, view_chunk: int = None, stats: dict = None,
 ):
     """B cameras over the same Gaussians.  intrs [B,4] (or [4], shared), extrs [B,3,4]|[B,4,4]
@@ -120,7 +120,7 @@ def rasterization_sh_views(
     ``grad_sync`` (view-batch data parallelism): a ``torch.distributed`` process group
     (or ``True`` for the default group).  The backward pass then returns the per-Gaussian gradients
     already SUMMED over the ranks of that group: the last preprocess-backward launch is cut into
-    ``grad_chunks`` slabs of Gaussians, and the sum all-reduce of a finished slab (one coalesced NCCL call for
+    ``grad_chunks`` slabs of Gaussians (default: 4 for two ranks, 2 beyond), and the sum all-reduce of a finished slab (one coalesced NCCL call for
     its five tensors, NCCL's own stream) runs under the kernels of the following slabs instead of after the
     whole backward.  Camera gradients stay local (every rank has its own cameras).  A callable is accepted as a
     custom reducer: it is called with every finished gradient slab (in place, sum semantics) and may return an
@@ -132,7 +132,7 @@ def rasterization_sh_views(
     vc = VIEW_CHUNK if view_chunk is None else int(view_chunk)
     images, radii = _RenderSHViews.apply(xyz, scale, rotate, opacity, shs, intrs, extrs, int(W), int(H), float(bg),
                                          float(sh_bias), bool(clamp), bool(with_depth), float(nearest), float(extent),
-                                         grad_sync, int(grad_chunks), ndc, bool(return_aux), vc, stats)
+                                         grad_sync, 0 if grad_chunks is None else int(grad_chunks), ndc, bool(return_aux), vc, stats)
     if return_aux:
         return images, radii, radii > 0
     return images
@@ -155,6 +155,17 @@ def _resolve_group(grad_sync):
         return None
     group = dist.group.WORLD if grad_sync is True else grad_sync
     return group if dist.get_world_size(group) > 1 else None
+
+
+def _default_grad_chunks(group) -> int:
+    """Slabs of the pipelined gradient exchange when the caller does not say.  Measured on B200 / NVSwitch, BASELINE
+    config #3, ms per step: 2 ranks 16.27 (2 slabs) vs 16.10 (4); 4 ranks 17.09 (2) / 17.60 (3) / 17.55 (4);
+    8 ranks 17.65 (1) / 17.23 (2) / 17.68 (4) -- the ring takes longer per call as it grows, and every extra call
+    competes with the backward kernels for the SMs."""
+    if callable(group):
+        return 2
+    import torch.distributed as dist
+    return 4 if dist.get_world_size(group) <= 2 else 2
 
 
 def _reduce_many(group, tensors, dev):
@@ -407,7 +418,8 @@ class _RenderSHViews(torch.autograd.Function):
                 # NCCL call, on NCCL's stream) runs under the kernels of the next slab
                 for k in range(len(chunks)):
                     blend_bwd(k)
-                nslab = max(1, min(int(ctx.grad_sync[1]), (P + 255) // 256))
+                nslab = int(ctx.grad_sync[1]) or _default_grad_chunks(group)
+                nslab = max(1, min(nslab, (P + 255) // 256))
                 step = ((P + nslab - 1) // nslab + 255) // 256 * 256  # slab starts stay 16-byte aligned
                 works = []
                 for lo in range(0, P, step):
