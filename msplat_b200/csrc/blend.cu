@@ -232,13 +232,18 @@ __global__ void __launch_bounds__(BL_NT) blend_fwd_kernel(const float4* __restri
 //     dL/dopacity = sum_p X                        dL/dfeature_k = sum_p w dpix_k(p)
 //     dL/du = -o (cx sum X dx + cy sum X dy)       dL/dv = -o (cz sum X dy + cy sum X dx)
 //     dL/dconic = -o (0.5 sum X dx^2, sum X dx dy, 0.5 sum X dy^2)         (:232-242)
-// Phase 1 (lane = pixel, as in the forward): replay the visits back to front and park (X, w) of
-// each visit in a per-warp shared-memory matrix [GQ Gaussians][32 pixels] (one STS.64 per visit).
-// Phase 2 (lane = Gaussian, every GQ = 16 visits): lane (g, h) walks 16 of the 32 pixels of
-// Gaussian g's row and accumulates the six moments and CH feature sums IN REGISTERS; the two
-// halves are combined with one shuffle per value and leave the SM as three vector reductions
-// (red.global.add.v4/.v2) per Gaussian.  No cross-lane reduction per visit, 10 instead of 26
-// shared-memory wavefronts per visit, ~75 instead of ~114 issue slots per visit (CH = 4).
+// Per staged batch of B list entries and per warp (8x4 pixels):
+// Pass 1 (lane = list slot): footprint test of the whole batch, the slots that pass are compacted in list
+// order into the warp's u16 hit list in shared memory.
+// Pass 2 / phase 1 (lane = pixel, as in the forward): walk the hit list two slots per iteration (their alpha
+// evaluations interleave), replay the visits that blend back to front and park (X, w) of each visit in a
+// per-warp shared-memory matrix [GQ Gaussians][32 pixels + pad] (one STS.64 per visit; lane 0 puts the
+// visit's staged slot into the pad cell).
+// Phase 2 (lane = Gaussian, every GQ = 16 visits): lane (g, h) walks 16 of the 32 pixels of Gaussian g's row
+// and accumulates raw moments about the block origin and CH feature sums IN REGISTERS, shifts the moments to
+// the Gaussian's centre, combines the two halves with one shuffle per value; the sums leave the SM as three
+// vector reductions (red.global.add.v4/.v2) per Gaussian.  No cross-lane reduction per visit; ~88 issue slots
+// per replayed warp-visit over the whole kernel (CH = 4; ncu, BASELINE config #3).
 constexpr int BW_GQ = 16;  // Gaussians per phase-2 group
 constexpr int BW_PS = 33;  // row stride of the (X, w) matrix in float2: conflict-free LDS.64 in both phases
 
@@ -564,12 +569,12 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float4* rec, const float
     return check_launch("alpha_blending_fwd");
 }
 
-// A/B switch for profiling runs (CH = 4), MSB_BWD_CFG.  Measured on BASELINE config #3
-// (profiles/r1_ab_experiments.md):
-//   default  256-entry batches, registers capped for 3 CTAs/SM (80)            1.054 ms
-//   1        128-entry batches, 3 CTAs/SM                                       1.11 ms
-//   2        256-entry batches, uncapped (93 registers -> 2 CTAs/SM)            1.19 ms
-//   3        128-entry batches, 64 registers (4 CTAs/SM, spills)                1.15 ms
+// A/B switch for profiling runs (CH = 4), MSB_BWD_CFG.  Measured on BASELINE config #3, ms per view
+// (profiles/r2_ab_experiments.md; round 1 in brackets):
+//   default  256-entry batches, registers capped for 3 CTAs/SM (80)            0.84  (1.054)
+//   1        128-entry batches, 3 CTAs/SM                                             (1.11)
+//   2        256-entry batches, uncapped (74 registers, 3 CTAs/SM)             0.91  (1.19 at 93 registers)
+//   3        128-entry batches, 64 registers (4 CTAs/SM, spills)               0.91  (1.15)
 // Fewer barriers per list entry beat the extra resident CTA.
 static int blend_bwd_cfg() {
     static const int v = [] { const char* e = getenv("MSB_BWD_CFG"); return e ? atoi(e) : 0; }();
