@@ -44,6 +44,10 @@ def _worker(rank, world, port, q):
         cams = orbit_cameras(6)
         total = render_view_batch(lambda e: _loss(xyz, w, e), cams, rank, world, grads)
         assert xyz.grad.data_ptr() == grads.flat.data_ptr()  # grads accumulated in place in the flat buffer
+        # slab count of the pipelined exchange when the caller gives none: 4 for two ranks (measured), 2 beyond
+        from msplat_b200.render import _default_grad_chunks, _resolve_group
+        assert _default_grad_chunks(_resolve_group(True)) == 4
+        assert _default_grad_chunks(lambda t: None) == 2
         q.put((rank, grads.flat.clone(), float(total)))
     finally:
         dist.destroy_process_group()
