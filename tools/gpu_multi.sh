@@ -1,16 +1,16 @@
 #!/bin/bash
-# Multi-GPU bench lines on one box: tools/gpu_multi.sh TAG "N|bench args" ...   (N = 1 runs without torchrun)
+# Multi-GPU bench lines on one box: tools/gpu_multi.sh TAG "N|bench args[|ENV=.. ENV=..]" ...   (N = 1 runs without torchrun)
 mkdir -p gpurun_out
 TAG=$1; shift
 i=0
 for spec in "$@"; do
-  IFS='|' read -r n bargs <<< "$spec"
+  IFS='|' read -r n bargs envs <<< "$spec"
   i=$((i+1))
   out=gpurun_out/multi_${TAG}_${i}_n${n}.json
   if [ "$n" = "1" ]; then
-    timeout 900 python bench.py --gpus 1 --no-cpu-baseline --no-steps-api --no-other-configs $bargs > $out 2> ${out%.json}.err
+    env $envs timeout 900 python bench.py --gpus 1 --no-cpu-baseline --no-steps-api --no-other-configs $bargs > $out 2> ${out%.json}.err
   else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+i)) \
+    env $envs timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+i)) \
       bench.py --gpus $n --no-cpu-baseline --no-steps-api --no-other-configs $bargs > $out 2> ${out%.json}.err
   fi
   python - "$out" "$n" "$bargs" <<'PY'
