@@ -214,3 +214,44 @@ def test_view_batch_chunking_host_logic():
     import pytest
     with pytest.raises(RuntimeError, match="2\\^31"):
         _split_for_sort([(0, 1)], [2 ** 31])
+
+
+def test_backward_blend_raw_moment_shift():
+    """csrc/blend.cu::bwd_reduce_group accumulates, per pixel row of a warp's 8x4 block, the raw moments
+    a = sum X, ax = sum X x, axx = sum X x^2 over the pixel columns x = 0..7 and shifts them once to the six moments
+    about the Gaussian's centre (dx = ux - x, dy = uy - row).  The same algebra in float32 numpy against the direct
+    float64 sums, for centres inside and far outside the block (the cancellation stays at rounding level because a
+    far centre makes the moments themselves large)."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for ux, uy in ((3.3, 1.7), (-40.5, 12.25), (250.0, -180.0), (0.0, 0.0)):
+        X = (rng.standard_normal((4, 8)) * rng.uniform(0.0, 1.0, (4, 8))).astype(np.float32)
+        xs = np.arange(8, dtype=np.float32)
+        m = np.zeros(6, dtype=np.float32)  # m0, mx, my, mxx, mxy, myy
+        for h in range(2):  # the two half-warps own rows 2h and 2h + 1
+            a = [np.float32(0)] * 2
+            ax = [np.float32(0)] * 2
+            axx = [np.float32(0)] * 2
+            for r in range(2):
+                for x in range(8):
+                    v = X[2 * h + r, x]
+                    a[r] = np.float32(a[r] + v)
+                    ax[r] = np.float32(ax[r] + v * xs[x])
+                    axx[r] = np.float32(axx[r] + v * xs[x] * xs[x])
+            u = np.float32(ux)
+            dy0 = np.float32(np.float32(uy) - np.float32(2 * h))
+            dy1 = np.float32(dy0 - np.float32(1))
+            s0, sx, sxx = np.float32(a[0] + a[1]), np.float32(ax[0] + ax[1]), np.float32(axx[0] + axx[1])
+            part = np.array([s0, u * s0 - sx, dy0 * a[0] + dy1 * a[1], u * (u * s0 - 2 * sx) + sxx,
+                             dy0 * (u * a[0] - ax[0]) + dy1 * (u * a[1] - ax[1]),
+                             dy0 * dy0 * a[0] + dy1 * dy1 * a[1]], dtype=np.float32)
+            m = (m + part).astype(np.float32)
+        Xd = X.astype(np.float64)
+        dx = ux - np.arange(8)[None, :]
+        dy = uy - np.arange(4)[:, None]
+        want = np.array([Xd.sum(), (Xd * dx).sum(), (Xd * dy).sum(), (Xd * dx * dx).sum(), (Xd * dx * dy).sum(),
+                         (Xd * dy * dy).sum()])
+        scale = np.array([np.abs(Xd).sum(), (np.abs(Xd) * np.abs(dx)).sum(), (np.abs(Xd) * np.abs(dy)).sum(),
+                          (np.abs(Xd) * dx * dx).sum(), (np.abs(Xd) * np.abs(dx * dy)).sum(),
+                          (np.abs(Xd) * dy * dy).sum()])
+        assert np.all(np.abs(m - want) <= 2e-5 * scale + 1e-12), (ux, uy, m, want)
